@@ -1,0 +1,234 @@
+// segment.cu -- row gathers and deterministic segmented reductions (HBM-bound kernels).
+// One warp owns one output row; a lane owns 4 consecutive columns per 128-column slab, so every
+// global access is a 128-bit (fp32) or 64-bit (bf16) vector and a warp reads whole 512 B / 256 B rows.
+#include "common.cuh"
+
+namespace aero {
+
+template <typename T>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const T* __restrict__ in, const int32_t* __restrict__ idx,
+                                                          const T* __restrict__ add, T* __restrict__ out,
+                                                          int64_t n_out, int width) {
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_out) return;
+  int lane = threadIdx.x & 31;
+  int64_t srow = idx ? (int64_t)idx[row] : row;
+  const T* ip = in + srow * width;
+  T* op = out + row * width;
+  const T* ap = add ? add + row * width : nullptr;
+  if ((width & 3) == 0) {
+    for (int c = lane * 4; c < width; c += 128) {
+      float4 v = load4(ip + c);
+      if (ap) {
+        float4 a = load4(ap + c);
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+      }
+      store4(op + c, v);
+    }
+  } else {
+    for (int c = lane; c < width; c += 32) {
+      float v = load1(ip + c);
+      if (ap) v += load1(ap + c);
+      store1(op + c, v);
+    }
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) segment_reduce_kernel(const TI* __restrict__ in, const int32_t* __restrict__ ptr,
+                                                             const int32_t* __restrict__ list, TO* __restrict__ out,
+                                                             int64_t n_seg, int width, int mean) {
+  int64_t seg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (seg >= n_seg) return;
+  int lane = threadIdx.x & 31;
+  int b = ptr[seg], e = ptr[seg + 1];
+  float scale = 1.f;
+  if (mean) scale = 1.f / (float)(e - b > 1 ? e - b : 1);
+  TO* op = out + seg * width;
+  if ((width & 3) == 0) {
+    for (int c = lane * 4; c < width; c += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int k = b;
+      // two rows in flight to overlap the index -> row dependency
+      for (; k + 1 < e; k += 2) {
+        int64_t r0 = list ? (int64_t)list[k] : (int64_t)k;
+        int64_t r1 = list ? (int64_t)list[k + 1] : (int64_t)k + 1;
+        float4 v0 = load4(in + r0 * width + c);
+        float4 v1 = load4(in + r1 * width + c);
+        acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+        acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+      }
+      if (k < e) {
+        int64_t r0 = list ? (int64_t)list[k] : (int64_t)k;
+        float4 v0 = load4(in + r0 * width + c);
+        acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+      }
+      if (mean) {
+        // divide (not multiply by reciprocal) to match scatter_mean = sum / count
+        float cnt = (float)(e - b > 1 ? e - b : 1);
+        acc.x /= cnt; acc.y /= cnt; acc.z /= cnt; acc.w /= cnt;
+      }
+      store4(op + c, acc);
+    }
+  } else {
+    for (int c = lane; c < width; c += 32) {
+      float acc = 0.f;
+      for (int k = b; k < e; ++k) {
+        int64_t r = list ? (int64_t)list[k] : (int64_t)k;
+        acc += load1(in + r * width + c);
+      }
+      if (mean) acc /= (float)(e - b > 1 ? e - b : 1);
+      store1(op + c, acc);
+    }
+  }
+  (void)scale;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) segment_bcast_kernel(const T* __restrict__ g_out, const int32_t* __restrict__ seg_of_row,
+                                                            const int32_t* __restrict__ ptr, T* __restrict__ g_in,
+                                                            int64_t n_rows, int width, int mean) {
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  int lane = threadIdx.x & 31;
+  int seg = seg_of_row[row];
+  float cnt = 1.f;
+  if (mean) {
+    int d = ptr[seg + 1] - ptr[seg];
+    cnt = (float)(d > 1 ? d : 1);
+  }
+  const T* ip = g_out + (int64_t)seg * width;
+  T* op = g_in + row * width;
+  if ((width & 3) == 0) {
+    for (int c = lane * 4; c < width; c += 128) {
+      float4 v = load4(ip + c);
+      if (mean) { v.x /= cnt; v.y /= cnt; v.z /= cnt; v.w /= cnt; }
+      store4(op + c, v);
+    }
+  } else {
+    for (int c = lane; c < width; c += 32) {
+      float v = load1(ip + c);
+      if (mean) v /= cnt;
+      store1(op + c, v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Receiver sums that straddle row tiles.  The block kernels write, per tile t, two fp32 partial
+// rows: part[t][0] = sum of the leading run when it is incomplete in t (started earlier or runs
+// past the end), part[t][1] = sum of the trailing run when it starts inside t and continues.
+// Node n with CSR range [b,e) spanning tiles t0 < t1 gets
+//     agg[n] = (b % R == 0 ? part[t0][0] : part[t0][1]) + part[t0+1..t1][0]   in that order.
+// One block per tile boundary; the block acts only if the run crossing the boundary starts in
+// the tile left of it (so each straddling node is handled exactly once).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) agg_fixup_kernel(const float* __restrict__ part, const int32_t* __restrict__ rowptr,
+                                                        const int32_t* __restrict__ dst, float* __restrict__ agg,
+                                                        int64_t rows, int tile_rows) {
+  int64_t t0 = blockIdx.x;
+  int64_t last_row = (t0 + 1) * tile_rows - 1;
+  if (last_row + 1 >= rows) return;  // no boundary after the final tile
+  int n = dst[last_row];
+  int b = rowptr[n], e = rowptr[n + 1];
+  if (e <= last_row + 1) return;          // run ends at the boundary: complete
+  if (b / tile_rows != t0) return;        // run started in an earlier tile: another block owns it
+  int64_t t1 = ((int64_t)e - 1) / tile_rows;
+  int c = threadIdx.x;
+  float acc = part[((size_t)t0 * 2 + ((b % tile_rows) == 0 ? 0 : 1)) * 128 + c];
+  for (int64_t t = t0 + 1; t <= t1; ++t) acc += part[((size_t)t * 2) * 128 + c];
+  agg[(size_t)n * 128 + c] = acc;
+}
+
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int n_parts, size_t stride,
+                                                              float* __restrict__ out, size_t n) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float acc = 0.f;
+  for (int p = 0; p < n_parts; ++p) acc += part[(size_t)p * stride + j];
+  out[j] = acc;
+}
+
+int launch_agg_fixup(const float* part, const int32_t* rowptr, float* agg, int64_t rows, int64_t n_nodes,
+                     int tile_rows, const int32_t* dst, cudaStream_t st) {
+  (void)n_nodes;
+  int64_t tiles = cdiv(rows, tile_rows);
+  if (tiles <= 1) return AERO_OK;
+  agg_fixup_kernel<<<(unsigned)(tiles - 1), 128, 0, st>>>(part, rowptr, dst, agg, rows, tile_rows);
+  AERO_LAUNCH_CHECK();
+  return AERO_OK;
+}
+
+int launch_reduce_partials(const float* part, int n_parts, size_t stride, float* out, size_t n, cudaStream_t st) {
+  if (n == 0) return AERO_OK;
+  reduce_partials_kernel<<<(unsigned)cdiv((int64_t)n, 256), 256, 0, st>>>(part, n_parts, stride, out, n);
+  AERO_LAUNCH_CHECK();
+  return AERO_OK;
+}
+
+}  // namespace aero
+
+using namespace aero;
+
+extern "C" int aero_gather_rows(const void* in, const int32_t* idx, const void* add, void* out, int64_t n_out,
+                                int64_t width, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AERO_CHECK_ARG(n_out >= 0 && width > 0 && width < (1 << 20), "aero_gather_rows: bad sizes");
+  if (n_out == 0) return AERO_OK;
+  AERO_CHECK_ARG(in && out, "aero_gather_rows: null pointer");
+  unsigned blocks = (unsigned)cdiv(n_out, 8);
+  if (dtype == AERO_F32)
+    gather_rows_kernel<float><<<blocks, 256, 0, st>>>((const float*)in, idx, (const float*)add, (float*)out, n_out, (int)width);
+  else if (dtype == AERO_BF16)
+    gather_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in, idx, (const __nv_bfloat16*)add,
+                                                               (__nv_bfloat16*)out, n_out, (int)width);
+  else {
+    set_error("aero_gather_rows: unsupported dtype %d", dtype);
+    return AERO_EUNSUPPORTED;
+  }
+  AERO_LAUNCH_CHECK();
+  return AERO_OK;
+}
+
+extern "C" int aero_segment_reduce(const void* in, const int32_t* ptr, const int32_t* list, void* out, int64_t n_seg,
+                                   int64_t width, int in_dtype, int out_dtype, int mean, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AERO_CHECK_ARG(n_seg >= 0 && width > 0 && width < (1 << 20), "aero_segment_reduce: bad sizes");
+  if (n_seg == 0) return AERO_OK;
+  AERO_CHECK_ARG(ptr && out, "aero_segment_reduce: null pointer");
+  unsigned blocks = (unsigned)cdiv(n_seg, 8);
+  int w = (int)width;
+  if (in_dtype == AERO_F32 && out_dtype == AERO_F32)
+    segment_reduce_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)in, ptr, list, (float*)out, n_seg, w, mean);
+  else if (in_dtype == AERO_BF16 && out_dtype == AERO_F32)
+    segment_reduce_kernel<__nv_bfloat16, float><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in, ptr, list, (float*)out, n_seg, w, mean);
+  else if (in_dtype == AERO_BF16 && out_dtype == AERO_BF16)
+    segment_reduce_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in, ptr, list, (__nv_bfloat16*)out, n_seg, w, mean);
+  else if (in_dtype == AERO_F32 && out_dtype == AERO_BF16)
+    segment_reduce_kernel<float, __nv_bfloat16><<<blocks, 256, 0, st>>>((const float*)in, ptr, list, (__nv_bfloat16*)out, n_seg, w, mean);
+  else {
+    set_error("aero_segment_reduce: unsupported dtypes %d -> %d", in_dtype, out_dtype);
+    return AERO_EUNSUPPORTED;
+  }
+  AERO_LAUNCH_CHECK();
+  return AERO_OK;
+}
+
+extern "C" int aero_segment_bcast(const void* g_out, const int32_t* seg_of_row, const int32_t* ptr, void* g_in,
+                                  int64_t n_rows, int64_t width, int dtype, int mean, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AERO_CHECK_ARG(n_rows >= 0 && width > 0 && width < (1 << 20), "aero_segment_bcast: bad sizes");
+  if (n_rows == 0) return AERO_OK;
+  AERO_CHECK_ARG(g_out && seg_of_row && g_in && (!mean || ptr), "aero_segment_bcast: null pointer");
+  unsigned blocks = (unsigned)cdiv(n_rows, 8);
+  if (dtype == AERO_F32)
+    segment_bcast_kernel<float><<<blocks, 256, 0, st>>>((const float*)g_out, seg_of_row, ptr, (float*)g_in, n_rows, (int)width, mean);
+  else if (dtype == AERO_BF16)
+    segment_bcast_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)g_out, seg_of_row, ptr, (__nv_bfloat16*)g_in, n_rows, (int)width, mean);
+  else {
+    set_error("aero_segment_bcast: unsupported dtype %d", dtype);
+    return AERO_EUNSUPPORTED;
+  }
+  AERO_LAUNCH_CHECK();
+  return AERO_OK;
+}

@@ -1,0 +1,55 @@
+"""Shared MLP + LayerNorm block (interface of reference models/mlp.py:5-51).
+
+Parameter names are the checkpoint contract: `layers.{i}.weight|bias` and `layer_norm.weight|bias`
+(SURVEY.md section 8b).  Inside a processor step the Linear/LayerNorm chain is executed by the fused
+block kernels (processor.py reads the parameters through `split_first` / `tail`); called on its own
+(encoders, decoder -- rows marked "next" in the scope table) it is a dense row-wise chain.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+class MLP(nn.Module):
+    def __init__(self, input_dim: int, hidden_dim: int, output_dim: int, num_hidden_layers: int = 1,
+                 activation_fn: str = "relu", dropout: float = 0.0, use_layer_norm: bool = True):
+        super().__init__()
+        self.use_layer_norm = use_layer_norm
+        self.activation_name = activation_fn
+        # getattr raises AttributeError for unknown names, like the reference (mlp.py:37)
+        self.activation = getattr(F, activation_fn)
+        if num_hidden_layers > 0:
+            widths = [input_dim] + [hidden_dim] * (num_hidden_layers + 1) + [output_dim]
+        else:
+            widths = [input_dim, output_dim]  # a single Linear, no activation (mlp.py:29-32)
+        self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(widths[:-1], widths[1:]))
+        if use_layer_norm:
+            self.layer_norm = nn.LayerNorm(output_dim)
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        last = len(self.layers) - 1
+        for i, lin in enumerate(self.layers):
+            x = lin(x)
+            if i < last:
+                x = self.dropout(self.activation(x))
+        return self.layer_norm(x) if self.use_layer_norm else x
+
+    # ---- views used by the fused processor path -------------------------------------------------
+    @property
+    def num_hidden(self) -> int:
+        """Number of Linear(hidden, hidden) layers between the first and the last Linear."""
+        return len(self.layers) - 2
+
+    def tail(self):
+        """(hidden [(W, b)...], W_out, b_out, gamma, beta) -- everything after the first Linear."""
+        hidden = [(l.weight, l.bias) for l in self.layers[1:-1]]
+        out = self.layers[-1]
+        if self.use_layer_norm:
+            gamma, beta = self.layer_norm.weight, self.layer_norm.bias
+        else:
+            gamma = torch.ones(out.out_features, device=out.weight.device, dtype=out.weight.dtype)
+            beta = torch.zeros_like(gamma)
+        return hidden, out.weight, out.bias, gamma, beta

@@ -1,0 +1,332 @@
+"""Tensor-level wrappers over the C ABI: graph plans, row gathers, segmented reductions, fused blocks.
+
+PyTorch is used for device memory and the current stream only; every function here requires CUDA
+tensors and raises otherwise (the north star forbids a CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import weakref
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from . import lib as _l
+
+D = 128
+
+
+def _require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "aero_gnn_b200: the message-passing path runs only on CUDA (sm_100a) tensors; "
+                f"got a tensor on {t.device} (no CPU fallback)"
+            )
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _l.AERO_F32
+    if t.dtype == torch.bfloat16:
+        return _l.AERO_BF16
+    raise RuntimeError(f"aero_gnn_b200: unsupported dtype {t.dtype} for the fused path (float32 and bfloat16 only)")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+class LaunchCounter:
+    """Counts kernels launched by this library (bench.py `gpu_launches`)."""
+
+    total = 0
+
+    @classmethod
+    def add(cls) -> None:
+        cls.total += _l.load().aero_last_launch_count()
+
+
+# ------------------------------------------------------------------------------------------------
+# graph plan
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class GraphPlan:
+    """Receiver-CSR + sender-CSR of one mesh (built once, cached)."""
+
+    E: int
+    N: int
+    rowptr: torch.Tensor   # [N+1] int32
+    perm: torch.Tensor     # [E] int32: caller edge id at CSR slot k
+    src: torch.Tensor      # [E] int32 sender of CSR slot
+    dst: torch.Tensor      # [E] int32 receiver of CSR slot
+    sptr: torch.Tensor     # [N+1] int32
+    sperm: torch.Tensor    # [E] int32 CSR slots grouped by sender
+    _inv_perm: Optional[torch.Tensor] = field(default=None, repr=False)
+    _inv_deg: Optional[torch.Tensor] = field(default=None, repr=False)
+
+    @property
+    def inv_perm(self) -> torch.Tensor:
+        """CSR slot of caller edge id (int32)."""
+        if self._inv_perm is None:
+            inv = torch.empty_like(self.perm)
+            inv[self.perm.long()] = torch.arange(self.E, dtype=torch.int32, device=self.perm.device)
+            self._inv_perm = inv
+        return self._inv_perm
+
+    @property
+    def inv_deg(self) -> torch.Tensor:
+        """1 / max(in-degree, 1) as fp32 [N] (scatter_mean divisor, mgnLayer.py:144)."""
+        if self._inv_deg is None:
+            deg = (self.rowptr[1:] - self.rowptr[:-1]).clamp(min=1).to(torch.float32)
+            self._inv_deg = 1.0 / deg
+        return self._inv_deg
+
+
+def build_graph_plan(edge_index: torch.Tensor, num_nodes: int) -> GraphPlan:
+    _require_cuda(edge_index)
+    if edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError("edge_index must have shape [2, E]")
+    lib = _l.load()
+    ei = edge_index.long().contiguous()
+    E, N = int(ei.size(1)), int(num_nodes)
+    dev = ei.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    rowptr = torch.empty(N + 1, **i32)
+    sptr = torch.empty(N + 1, **i32)
+    perm, src, dst, sperm = (torch.empty(E, **i32) for _ in range(4))
+    status = torch.zeros(4, **i32)
+    ws = _workspace(lib.aero_graph_plan_workspace_bytes(E, N), dev)
+    with torch.cuda.device(dev):
+        rc = lib.aero_graph_plan_build(_ptr(ei), E, N, _ptr(rowptr), _ptr(perm), _ptr(src), _ptr(dst), _ptr(sptr),
+                                       _ptr(sperm), _ptr(status), _ptr(ws), ws.numel(), _stream())
+    _l.check(rc, "aero_graph_plan_build")
+    bad = int(status[0].item())
+    if bad:
+        raise IndexError(f"edge_index holds {bad} entries outside [0, {N})")
+    return GraphPlan(E, N, rowptr, perm, src, dst, sptr, sperm)
+
+
+def content_hash(t: torch.Tensor) -> int:
+    _require_cuda(t)
+    lib = _l.load()
+    t = t.contiguous()
+    nbytes = t.numel() * t.element_size()
+    if nbytes % 8:
+        raise ValueError("content_hash needs a multiple of 8 bytes")
+    out = torch.zeros(1, dtype=torch.int64, device=t.device)
+    with torch.cuda.device(t.device):
+        rc = lib.aero_hash_u64(_ptr(t), nbytes, _ptr(out), _stream())
+    _l.check(rc, "aero_hash_u64")
+    return int(out.item())
+
+
+class PlanCache:
+    """Graph plans keyed by mesh connectivity.
+
+    Fast path: the same live tensor object at the same version -> no device work at all.
+    Otherwise a 64-bit content hash of edge_index (one pass over 16E bytes + one 8-byte readback)
+    finds the plan of a mesh seen before (DataLoader epochs revisit the same meshes).
+    """
+
+    def __init__(self, capacity: int = 64):
+        self.capacity = capacity
+        self._by_hash: "OrderedDict[tuple, GraphPlan]" = OrderedDict()
+        self._last = None  # (weakref, version, ptr, N, plan)
+
+    def get(self, edge_index: torch.Tensor, num_nodes: int) -> GraphPlan:
+        last = self._last
+        if last is not None:
+            ref, ver, ptr, n, plan = last
+            if ref() is edge_index and ver == edge_index._version and ptr == edge_index.data_ptr() and n == num_nodes:
+                return plan
+        ei = edge_index.long().contiguous()
+        key = (content_hash(ei), int(ei.size(1)), int(num_nodes), str(ei.device))
+        plan = self._by_hash.get(key)
+        if plan is None:
+            plan = build_graph_plan(ei, num_nodes)
+            self._by_hash[key] = plan
+            while len(self._by_hash) > self.capacity:
+                self._by_hash.popitem(last=False)
+        else:
+            self._by_hash.move_to_end(key)
+        try:
+            self._last = (weakref.ref(edge_index), edge_index._version, edge_index.data_ptr(), num_nodes, plan)
+        except TypeError:
+            self._last = None
+        return plan
+
+    def clear(self) -> None:
+        self._by_hash.clear()
+        self._last = None
+
+
+PLAN_CACHE = PlanCache()
+
+
+# ------------------------------------------------------------------------------------------------
+# gathers / segmented reductions
+# ------------------------------------------------------------------------------------------------
+def gather_rows(inp: torch.Tensor, idx: Optional[torch.Tensor], add: Optional[torch.Tensor] = None,
+                n_out: Optional[int] = None) -> torch.Tensor:
+    """out[i] = inp[idx[i]] (+ add[i]).  idx int32 (None = identity)."""
+    _require_cuda(inp, idx, add)
+    lib = _l.load()
+    inp = inp.contiguous()
+    n = int(idx.numel()) if idx is not None else (int(n_out) if n_out is not None else inp.size(0))
+    width = inp.size(1)
+    out = torch.empty((n, width), dtype=inp.dtype, device=inp.device)
+    if add is not None:
+        add = add.contiguous()
+        assert add.shape == out.shape and add.dtype == inp.dtype
+    with torch.cuda.device(inp.device):
+        rc = lib.aero_gather_rows(_ptr(inp), _ptr(idx), _ptr(add), _ptr(out), n, width, dtype_code(inp), _stream())
+    _l.check(rc, "aero_gather_rows")
+    LaunchCounter.add()
+    return out
+
+
+def segment_reduce(inp: torch.Tensor, ptr: torch.Tensor, lst: Optional[torch.Tensor], n_seg: int,
+                   mean: bool = False, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """out[n] = sum (or mean) of inp[lst[k]] for k in [ptr[n], ptr[n+1]); fixed order, fp32 accumulate."""
+    _require_cuda(inp, ptr, lst)
+    lib = _l.load()
+    inp = inp.contiguous()
+    width = inp.size(1)
+    out = torch.empty((n_seg, width), dtype=out_dtype or inp.dtype, device=inp.device)
+    with torch.cuda.device(inp.device):
+        rc = lib.aero_segment_reduce(_ptr(inp), _ptr(ptr), _ptr(lst), _ptr(out), n_seg, width, dtype_code(inp),
+                                     dtype_code(out), int(mean), _stream())
+    _l.check(rc, "aero_segment_reduce")
+    LaunchCounter.add()
+    return out
+
+
+def segment_bcast(g_out: torch.Tensor, seg_of_row: torch.Tensor, ptr: Optional[torch.Tensor], mean: bool) -> torch.Tensor:
+    _require_cuda(g_out, seg_of_row, ptr)
+    lib = _l.load()
+    g_out = g_out.contiguous()
+    n, width = int(seg_of_row.numel()), g_out.size(1)
+    g_in = torch.empty((n, width), dtype=g_out.dtype, device=g_out.device)
+    with torch.cuda.device(g_out.device):
+        rc = lib.aero_segment_bcast(_ptr(g_out), _ptr(seg_of_row), _ptr(ptr), _ptr(g_in), n, width, dtype_code(g_out),
+                                    int(mean), _stream())
+    _l.check(rc, "aero_segment_bcast")
+    LaunchCounter.add()
+    return g_in
+
+
+# ------------------------------------------------------------------------------------------------
+# fused block
+# ------------------------------------------------------------------------------------------------
+def packed_floats(L: int) -> int:
+    return (L + 2) * D * D + (L + 3) * D
+
+
+def choose_path(dtype: torch.dtype, act: str) -> int:
+    """bf16 rows run on tcgen05 when the library has it; fp32 rows run the exact CUDA-core path."""
+    if os.environ.get("AERO_FORCE_SIMT", "0") == "1":
+        return _l.AERO_PATH_SIMT
+    if dtype == torch.bfloat16 and act == "relu" and _l.load().aero_has_umma():
+        return _l.AERO_PATH_UMMA
+    return _l.AERO_PATH_SIMT
+
+
+class PreparedBlock:
+    """Device image of one block's weights for a kernel path (rebuilt when the weights change)."""
+
+    def __init__(self, w_packed: torch.Tensor, L: int, path: int, act: str, use_ln: bool):
+        _require_cuda(w_packed)
+        if act not in _l.ACT_CODES:
+            raise RuntimeError(
+                f"aero_gnn_b200: activation '{act}' is not supported by the fused sm_100a path "
+                f"(supported: {sorted(_l.ACT_CODES)})"
+            )
+        lib = _l.load()
+        assert w_packed.dtype == torch.float32 and w_packed.numel() == packed_floats(L)
+        self.L, self.path, self.act, self.use_ln = L, path, _l.ACT_CODES[act], int(use_ln)
+        self.w = w_packed.contiguous()
+        self.buf = _workspace(lib.aero_block_prepared_bytes(L, path), w_packed.device)
+        with torch.cuda.device(w_packed.device):
+            rc = lib.aero_block_prepare(_ptr(self.w), L, path, _ptr(self.buf), _stream())
+        _l.check(rc, "aero_block_prepare")
+        LaunchCounter.add()
+
+
+def _desc(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, main_scale=None, rowptr=None, n_nodes=0):
+    d = _l.BlockDesc()
+    d.dtype = dtype_code(P)
+    d.path = prep.path
+    d.L = prep.L
+    d.act = prep.act
+    d.use_ln = prep.use_ln
+    d.main_f32 = int(main.dtype == torch.float32 and P.dtype != torch.float32)
+    d.rows = main.size(0)
+    d.n_nodes = n_nodes
+    d.ldp = P.size(1)
+    d.poff0, d.poff1 = poff0, poff1
+    d.main = main.data_ptr()
+    d.main_scale = main_scale.data_ptr() if main_scale is not None else None
+    d.resid = resid.data_ptr() if resid is not None else None
+    d.P = P.data_ptr()
+    d.idx0 = idx0.data_ptr() if idx0 is not None else None
+    d.idx1 = idx1.data_ptr() if idx1 is not None else None
+    d.rowptr = rowptr.data_ptr() if rowptr is not None else None
+    d.prepared = prep.buf.data_ptr()
+    return d
+
+
+def block_fwd(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, main_scale=None, rowptr=None,
+              want_agg=False):
+    """Forward of one fused block; returns (out, agg or None)."""
+    _require_cuda(main, resid, P)
+    lib = _l.load()
+    n_nodes = P.size(0)
+    d = _desc(prep, main, resid, P, idx0, idx1, poff0, poff1, main_scale=main_scale, rowptr=rowptr, n_nodes=n_nodes)
+    out = torch.empty((main.size(0), D), dtype=P.dtype, device=P.device)
+    agg = torch.empty((n_nodes, D), dtype=torch.float32, device=P.device) if want_agg else None
+    d.out = out.data_ptr()
+    d.agg = agg.data_ptr() if agg is not None else None
+    ws = _workspace(lib.aero_block_workspace_bytes(C.byref(d), 0), P.device)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+    with torch.cuda.device(P.device):
+        rc = lib.aero_block_fwd(C.byref(d), _stream())
+    _l.check(rc, "aero_block_fwd")
+    LaunchCounter.add()
+    return out, agg
+
+
+def block_bwd(prep: PreparedBlock, main, P, idx0, idx1, poff0, poff1, g_out, *, g_agg=None, main_scale=None,
+              has_resid_grad=False, g_main_out: Optional[torch.Tensor] = None):
+    """Backward of one fused block; returns (g_main, g_h0, g_w_packed[fp32], W_main slot zero)."""
+    _require_cuda(main, P, g_out)
+    lib = _l.load()
+    d = _desc(prep, main, None, P, idx0, idx1, poff0, poff1, main_scale=main_scale, n_nodes=P.size(0))
+    rows = main.size(0)
+    g_main = g_main_out if g_main_out is not None else torch.empty((rows, D), dtype=main.dtype, device=P.device)
+    g_h0 = torch.empty((rows, D), dtype=P.dtype, device=P.device)
+    g_w = torch.zeros(packed_floats(prep.L), dtype=torch.float32, device=P.device)
+    d.has_resid_grad = int(has_resid_grad)
+    d.g_out = g_out.data_ptr()
+    d.g_agg = g_agg.data_ptr() if g_agg is not None else None
+    d.g_main = g_main.data_ptr()
+    d.g_h0 = g_h0.data_ptr()
+    d.g_w = g_w.data_ptr()
+    ws = _workspace(lib.aero_block_workspace_bytes(C.byref(d), 1), P.device)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+    with torch.cuda.device(P.device):
+        rc = lib.aero_block_bwd(C.byref(d), _stream())
+    _l.check(rc, "aero_block_bwd")
+    LaunchCounter.add()
+    return g_main, g_h0, g_w

@@ -1,0 +1,233 @@
+"""MGN processor stack: K message-passing steps on one mesh as a single autograd node.
+
+Follows models/mgnLayer.py:177-213 (one step) and the layer loops of models/mgn.py:127-128,
+bsms_mgn.py:156-159/188-191/208-211 of the reference.  Per step (edge latents kept in
+receiver-CSR order, see ops.GraphPlan):
+
+    P      = x @ [W_s; W_d; W_nx]^T + [0; b_e0; b_n0]           node pre-projection (sum trick,
+                                                                mgnLayer.py:97-103), plain GEMM
+    e'     = e + LN(MLP_e(e W_e^T + P_s[src] + P_d[dst]))       fused edge block  (mgnLayer.py:192,205)
+    agg    = segment_sum(e', receiver)                          fused into the edge block (:146)
+    x'     = x + LN(MLP_n(agg W_na^T + P_n))                    fused node block  (mgnLayer.py:208,211)
+
+Backward recomputes each block from the saved layer inputs (x, e) and the fp32 aggregate; no MLP
+activation is kept (reference autograd keeps all of them).  Gradients of gathered node rows are
+reduced by receiver-CSR / sender-CSR segmented sums -- no atomics anywhere.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+
+D = ops.D
+
+
+@dataclass
+class StepWeights:
+    """Packed parameters of one processor step (all tensors differentiable functions of the module params)."""
+
+    w_edge: torch.Tensor   # fp32 [packed_floats(L_e)]  W_main = W_e
+    w_node: torch.Tensor   # fp32 [packed_floats(L_n)]  W_main = W_n[:, D:2D] (aggregate half)
+    w_proj: torch.Tensor   # [3D, D] latent dtype: [W_s; W_d; W_n[:, :D]]
+    b_proj: torch.Tensor   # [3D]    latent dtype: [0; b_e0; b_n0]
+
+
+@dataclass
+class StackConfig:
+    L_edge: int
+    L_node: int
+    act_edge: str
+    act_node: str
+    use_ln: bool = True
+    mean: bool = False      # aggregation == 'mean' (mgnLayer.py:143-144)
+
+
+def pack_block(w_main, hidden: Sequence, w_out, b_out, gamma, beta) -> torch.Tensor:
+    """[W_main | W_1..W_L | W_out | b_1..b_L | b_out | gamma | beta] as one fp32 vector."""
+    parts = [w_main.reshape(-1)] + [w.reshape(-1) for (w, _) in hidden] + [w_out.reshape(-1)]
+    parts += [b.reshape(-1) for (_, b) in hidden] + [b_out.reshape(-1), gamma.reshape(-1), beta.reshape(-1)]
+    return torch.cat([p.float() for p in parts])
+
+
+class MGNStackFn(torch.autograd.Function):
+    """apply(cfg, plan, x, e_csr, *flat) with flat = (w_edge, w_node, w_proj, b_proj) per step."""
+
+    @staticmethod
+    def forward(ctx, cfg: StackConfig, plan: ops.GraphPlan, x: torch.Tensor, e: torch.Tensor, *flat):
+        ops._require_cuda(x, e)
+        if x.dtype != e.dtype:
+            raise RuntimeError(f"node latents are {x.dtype} but edge latents are {e.dtype}")
+        ops.dtype_code(x)
+        if x.size(1) != D or e.size(1) != D:
+            raise RuntimeError(f"the fused sm_100a path supports latent width {D} only (got {x.size(1)}, {e.size(1)})")
+        if x.size(0) != plan.N or e.size(0) != plan.E:
+            raise RuntimeError("latent shapes do not match the graph plan")
+        K = len(flat) // 4
+        x = x.contiguous()
+        e = e.contiguous()
+        path_e = ops.choose_path(x.dtype, cfg.act_edge)
+        path_n = ops.choose_path(x.dtype, cfg.act_node)
+        scale = plan.inv_deg if cfg.mean else None
+        saved = []
+        for k in range(K):
+            w_edge, w_node, w_proj, b_proj = flat[4 * k: 4 * k + 4]
+            pe = ops.PreparedBlock(w_edge.detach(), cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
+            pn = ops.PreparedBlock(w_node.detach(), cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
+            P = torch.addmm(b_proj.detach(), x, w_proj.detach().t())
+            e_new, agg = ops.block_fwd(pe, e, e, P, plan.src, plan.dst, 0, D, rowptr=plan.rowptr, want_agg=True)
+            x_new, _ = ops.block_fwd(pn, agg, x, P, None, None, 2 * D, 0, main_scale=scale)
+            saved += [x, e, agg]
+            x, e = x_new, e_new
+        ctx.cfg, ctx.plan, ctx.K = cfg, plan, K
+        ctx.paths = (path_e, path_n)
+        ctx.save_for_backward(*saved, *flat)
+        return x, e
+
+    @staticmethod
+    def backward(ctx, G_x, G_e):
+        cfg, plan, K = ctx.cfg, ctx.plan, ctx.K
+        path_e, path_n = ctx.paths
+        saved = ctx.saved_tensors
+        acts, flat = saved[: 3 * K], saved[3 * K:]
+        dt = acts[0].dtype
+        G_x = G_x.contiguous().to(dt)
+        G_e = G_e.contiguous().to(dt).clone()
+        scale = plan.inv_deg if cfg.mean else None
+        grads: List[Optional[torch.Tensor]] = [None] * (4 * K)
+        for k in reversed(range(K)):
+            x, e, agg = acts[3 * k: 3 * k + 3]
+            w_edge, w_node, w_proj, b_proj = flat[4 * k: 4 * k + 4]
+            pe = ops.PreparedBlock(w_edge, cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
+            pn = ops.PreparedBlock(w_node, cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
+            P = torch.addmm(b_proj, x, w_proj.t())
+            # node block: g_agg, gradient of the node pre-activation, MLP weight grads
+            g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale)
+            agg_eff = agg if scale is None else agg * scale[:, None]
+            g_wn[: D * D] = (g_h0n.float().t() @ agg_eff).reshape(-1)
+            # edge block: total gradient of e' = G_e + g_agg[receiver]
+            G_e, g_h0e, g_we = ops.block_bwd(pe, e, P, plan.src, plan.dst, 0, D, G_e, g_agg=g_agg,
+                                             has_resid_grad=True, g_main_out=G_e)
+            g_we[: D * D] = (g_h0e.t() @ e).float().reshape(-1)
+            # gradients of the gathered projections: segmented sums by sender and by receiver
+            g_ps = ops.segment_reduce(g_h0e, plan.sptr, plan.sperm, plan.N)
+            g_pd = ops.segment_reduce(g_h0e, plan.rowptr, None, plan.N)
+            w_s, w_d, w_nx = w_proj[:D], w_proj[D:2 * D], w_proj[2 * D:]
+            g_x = G_x.clone()
+            g_x.addmm_(g_ps, w_s)
+            g_x.addmm_(g_pd, w_d)
+            g_x.addmm_(g_h0n, w_nx)
+            g_wproj = torch.cat([g_ps.t() @ x, g_pd.t() @ x, g_h0n.t() @ x], dim=0)
+            g_bproj = torch.cat([g_ps.float().sum(0), g_pd.float().sum(0), g_h0n.float().sum(0)]).to(dt)
+            grads[4 * k: 4 * k + 4] = [g_we, g_wn, g_wproj.to(w_proj.dtype), g_bproj.to(b_proj.dtype)]
+            G_x = g_x
+        return (None, None, G_x, G_e, *grads)
+
+
+def run_stack(cfg: StackConfig, plan: ops.GraphPlan, x: torch.Tensor, e_csr: torch.Tensor,
+              steps: Sequence[StepWeights]):
+    flat = []
+    for s in steps:
+        flat += [s.w_edge, s.w_node, s.w_proj, s.b_proj]
+    return MGNStackFn.apply(cfg, plan, x, e_csr, *flat)
+
+
+class PermuteRowsFn(torch.autograd.Function):
+    """out[i] = inp[idx[i]] for a permutation idx (int32); backward gathers with the inverse."""
+
+    @staticmethod
+    def forward(ctx, inp, idx, inv_idx):
+        ctx.inv_idx = inv_idx
+        return ops.gather_rows(inp, idx)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.gather_rows(g.contiguous(), ctx.inv_idx), None, None
+
+
+def permute_rows(inp: torch.Tensor, idx: torch.Tensor, inv_idx: torch.Tensor) -> torch.Tensor:
+    return PermuteRowsFn.apply(inp, idx, inv_idx)
+
+
+class SingleBlockFn(torch.autograd.Function):
+    """One fused block without residual: the standalone EdgeBlock / EdgeBlockSum / NodeBlock forward
+    (mgnLayer.py:32-49, :93-105, :134-153).  `e` is in receiver-CSR order."""
+
+    @staticmethod
+    def forward(ctx, mode: str, L: int, act: str, use_ln: bool, mean: bool, plan: ops.GraphPlan, e, x, w, w_proj,
+                b_proj):
+        ops._require_cuda(e, x)
+        if x.dtype != e.dtype:
+            raise RuntimeError(f"node latents are {x.dtype} but edge latents are {e.dtype}")
+        if x.size(1) != D or e.size(1) != D:
+            raise RuntimeError(f"the fused sm_100a path supports latent width {D} only")
+        e, x = e.contiguous(), x.contiguous()
+        path = ops.choose_path(x.dtype, act)
+        prep = ops.PreparedBlock(w.detach(), L, path, act, use_ln)
+        P = torch.addmm(b_proj.detach(), x, w_proj.detach().t())
+        scale = plan.inv_deg if (mean and mode == "node") else None
+        if mode == "edge":
+            agg = None
+            out, _ = ops.block_fwd(prep, e, None, P, plan.src, plan.dst, 0, D)
+        else:
+            agg = ops.segment_reduce(e, plan.rowptr, None, plan.N, out_dtype=torch.float32)
+            out, _ = ops.block_fwd(prep, agg, None, P, None, None, 0, 0, main_scale=scale)
+        ctx.meta = (mode, L, act, use_ln, path, plan, scale)
+        ctx.save_for_backward(e, x, agg if agg is not None else e.new_empty(0), w, w_proj, b_proj)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        mode, L, act, use_ln, path, plan, scale = ctx.meta
+        e, x, agg, w, w_proj, b_proj = ctx.saved_tensors
+        dt = x.dtype
+        g = g.contiguous().to(dt)
+        prep = ops.PreparedBlock(w, L, path, act, use_ln)
+        P = torch.addmm(b_proj, x, w_proj.t())
+        if mode == "edge":
+            g_e, g_h0, g_w = ops.block_bwd(prep, e, P, plan.src, plan.dst, 0, D, g)
+            g_w[: D * D] = (g_h0.t() @ e).float().reshape(-1)
+            g_ps = ops.segment_reduce(g_h0, plan.sptr, plan.sperm, plan.N)
+            g_pd = ops.segment_reduce(g_h0, plan.rowptr, None, plan.N)
+            g_x = torch.addmm(g_ps @ w_proj[:D], g_pd, w_proj[D:])
+            g_wproj = torch.cat([g_ps.t() @ x, g_pd.t() @ x], dim=0)
+            g_b = torch.cat([g_ps.float().sum(0), g_pd.float().sum(0)]).to(b_proj.dtype)
+        else:
+            g_agg, g_h0, g_w = ops.block_bwd(prep, agg, P, None, None, 0, 0, g, main_scale=scale)
+            agg_eff = agg if scale is None else agg * scale[:, None]
+            g_w[: D * D] = (g_h0.float().t() @ agg_eff).reshape(-1)
+            g_e = ops.gather_rows(g_agg.to(dt), plan.dst)
+            g_x = g_h0 @ w_proj
+            g_wproj = g_h0.t() @ x
+            g_b = g_h0.float().sum(0).to(b_proj.dtype)
+        return (None,) * 6 + (g_e, g_x, g_w, g_wproj.to(w_proj.dtype), g_b)
+
+
+def _plan_and_csr(edge_attr, node_attr, edge_index):
+    ops._require_cuda(node_attr, edge_attr, edge_index)
+    plan = ops.PLAN_CACHE.get(edge_index, node_attr.size(0))
+    return plan, permute_rows(edge_attr, plan.perm, plan.inv_perm)
+
+
+def edge_block_apply(parts: dict, edge_attr, node_attr, edge_index):
+    """Standalone edge block: returns the edge update in the caller's edge order (no residual)."""
+    plan, e_csr = _plan_and_csr(edge_attr, node_attr, edge_index)
+    dt = node_attr.dtype
+    w = pack_block(parts["w_e"], parts["hidden"], parts["w_out"], parts["b_out"], parts["gamma"], parts["beta"])
+    w_proj = torch.cat([parts["w_s"], parts["w_d"]], dim=0).to(dt)
+    b_proj = torch.cat([torch.zeros_like(parts["b0"]), parts["b0"]]).to(dt)
+    u = SingleBlockFn.apply("edge", len(parts["hidden"]), parts["act"], parts["use_ln"], False, plan, e_csr, node_attr,
+                            w, w_proj, b_proj)
+    return permute_rows(u, plan.inv_perm, plan.perm)
+
+
+def node_block_apply(parts: dict, node_attr, edge_attr, edge_index, mean: bool):
+    """Standalone node block: aggregate incoming edge rows, return the node update (no residual)."""
+    plan, e_csr = _plan_and_csr(edge_attr, node_attr, edge_index)
+    dt = node_attr.dtype
+    w = pack_block(parts["w_a"], parts["hidden"], parts["w_out"], parts["b_out"], parts["gamma"], parts["beta"])
+    return SingleBlockFn.apply("node", len(parts["hidden"]), parts["act"], parts["use_ln"], mean, plan, e_csr, node_attr,
+                               w, parts["w_x"].to(dt), parts["b0"].to(dt))

@@ -1,0 +1,209 @@
+/*
+ * aero_gnn.h -- C-ABI of libaero_sm100.so: the B200 (sm_100a) implementation of the
+ * MeshGraphNets message-passing hot path of cudagu/aero-gnn.
+ *
+ * The reference has no FFI: its boundary for this path is the Python nn.Module API
+ * (SURVEY.md section 8b).  This header is therefore the *new* native boundary the Python
+ * modules in aero_gnn_b200/models bind through ctypes; every entry point cites the
+ * reference call site (file:line under the reference checkout) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every buffer is allocated and owned by the caller (PyTorch); pointers are raw device
+ *     pointers; no function allocates, frees, or synchronises the device;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - sizes are int64_t, graph indices handed to kernels are int32_t (E, N < 2^31);
+ *   - return value 0 = ok, otherwise an AERO_E* code; aero_last_error() gives the text
+ *     (thread-local);
+ *   - latent width is fixed at AERO_D = 128 (config.yaml:42 hidden_dim 128) for the fused
+ *     block kernels; other widths are rejected with AERO_EUNSUPPORTED (no fallback).
+ */
+#ifndef AERO_GNN_H_
+#define AERO_GNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AERO_D 128
+
+/* error codes */
+#define AERO_OK 0
+#define AERO_EINVAL 1        /* bad argument (null pointer, negative size, ...)           */
+#define AERO_EUNSUPPORTED 2  /* dtype / width / activation outside the fused path         */
+#define AERO_ECUDA 3         /* a CUDA runtime call or kernel launch failed               */
+#define AERO_EWORKSPACE 4    /* workspace too small                                       */
+
+/* storage dtype of latent rows */
+#define AERO_F32 0
+#define AERO_BF16 1
+
+/* activations whose derivative is a function of the activation output
+ * (mlp.py:37 getattr(F, activation_fn); mgnLayer.py:81 hard-codes ReLU for EdgeBlockSum) */
+#define AERO_ACT_RELU 0
+#define AERO_ACT_TANH 1
+#define AERO_ACT_SIGMOID 2
+#define AERO_ACT_ELU 3
+#define AERO_ACT_LEAKY_RELU 4
+
+/* which kernel family executes a block: SIMT = fp32 CUDA-core math (exact fp32 parity path),
+ * UMMA = bf16 tcgen05 tensor-core tiles with fp32 accumulation in TMEM. */
+#define AERO_PATH_SIMT 0
+#define AERO_PATH_UMMA 1
+
+const char* aero_last_error(void);
+int aero_version(void);
+/* 1 when the library was compiled with the tcgen05 (UMMA) kernels */
+int aero_has_umma(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph plan: receiver-CSR + sender-CSR, built once per mesh.
+ * Replaces the per-step index work of mgnLayer.py:39-41 (row/col gathers), :101 and the
+ * atomics of torch_scatter.scatter_add at mgnLayer.py:146.
+ *
+ *   edge_index  [2,E] int64 (row 0 = sender, row 1 = receiver), any order, duplicates and
+ *               self-loops allowed (bsms_mgn.py:280-288 produces both).
+ *   rowptr      [N+1]  receiver-CSR offsets
+ *   perm        [E]    perm[k] = caller edge id stored at CSR slot k (stable: ascending id
+ *                      inside one receiver, i.e. the order CPU scatter_add_ accumulates in)
+ *   src, dst    [E]    sender / receiver of CSR slot k
+ *   sptr        [N+1]  sender-CSR offsets
+ *   sperm       [E]    CSR slots whose sender is n, ascending, for n = 0..N-1
+ *   status      [4]    device int32: [0] = number of out-of-range indices found
+ * ------------------------------------------------------------------------------------------ */
+size_t aero_graph_plan_workspace_bytes(int64_t E, int64_t N);
+int aero_graph_plan_build(const int64_t* edge_index, int64_t E, int64_t N,
+                          int32_t* rowptr, int32_t* perm, int32_t* src, int32_t* dst,
+                          int32_t* sptr, int32_t* sperm, int32_t* status,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stable LSD radix sort of (key,value) pairs, `key_bits` low bits significant.
+ * keys_out/vals_out receive the result; keys_in/vals_in are clobbered.  Building block of the
+ * plan and of the bistride index kernels (replaces torch.argsort bsms_mgn.py:242 and the
+ * sort inside torch.unique bsms_mgn.py:280). */
+size_t aero_sort_pairs_workspace_bytes(int64_t n);
+int aero_sort_pairs_u64(uint64_t* keys_in, int32_t* vals_in, uint64_t* keys_out, int32_t* vals_out,
+                        int64_t n, int key_bits, void* workspace, size_t workspace_bytes, void* stream);
+
+/* 64-bit content hash of a device buffer (plan-cache key); result written to out[0] (device). */
+int aero_hash_u64(const void* data, int64_t nbytes, uint64_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row gathers / segmented reductions (deterministic, no atomics).
+ * ------------------------------------------------------------------------------------------ */
+/* out[i,:] = in[idx[i],:]            (mgnLayer.py:40-41 node_attr[row]; bsms_mgn.py:306 unpool)
+ * if add != NULL: out[i,:] = in[idx[i],:] + add[i,:]   (bsms_mgn.py:199-200 unpool + skip) */
+int aero_gather_rows(const void* in, const int32_t* idx, const void* add, void* out,
+                     int64_t n_out, int64_t width, int dtype, void* stream);
+/* out[n,:] = scale(n) * sum_{k in [ptr[n],ptr[n+1])} in[list ? list[k] : k, :]
+ *   mean=0: scale = 1 (scatter_add, mgnLayer.py:146); mean=1: scale = 1/max(count,1)
+ *   (scatter_mean, mgnLayer.py:144, bsms_mgn.py:265-272,283).  fp32 accumulation in list order.
+ *   out_dtype may differ from in_dtype (fp32 aggregates of bf16 rows). */
+int aero_segment_reduce(const void* in, const int32_t* ptr, const int32_t* list, void* out,
+                        int64_t n_seg, int64_t width, int in_dtype, int out_dtype, int mean,
+                        void* stream);
+/* backward of the mean/sum reduce w.r.t. `in`: g_in[i,:] = scale(seg[i]) * g_out[seg[i],:] */
+int aero_segment_bcast(const void* g_out, const int32_t* seg_of_row, const int32_t* ptr,
+                       void* g_in, int64_t n_rows, int64_t width, int dtype, int mean, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused MGN block (edge block or node block of one processor step).
+ *
+ * forward, per row r (an edge in receiver-CSR order, or a node):
+ *     h0 = act( main[r] @ W_main^T + P[idx0[r], poff0:poff0+128] (+ P[idx1[r], poff1:...]) )
+ *     h_l = act( h_{l-1} @ W_l^T + b_l )                    l = 1..L
+ *     y   = h_L @ W_out^T + b_out ;  u = LayerNorm(y) * gamma + beta   (mlp.py:41-49, eps 1e-5)
+ *     out[r] = resid[r] + u                                  (mgnLayer.py:205 / :211)
+ *   and, when agg != NULL (edge block), agg[n] = sum of out[r] over the CSR rows of receiver n
+ *   (mgnLayer.py:146), accumulated in CSR order in fp32.
+ *
+ *   The first Linear of the reference block (mgnLayer.py:26-30 EdgeBlock.mlp.layers[0],
+ *   :97-103 EdgeBlockSum, :151-153 NodeBlock) is split as  [W_main | W_gathered...]: the
+ *   gathered part is pre-projected per node into P (sum trick of mgnLayer.py:97-103), bias
+ *   included, by the caller with a plain GEMM.
+ *
+ * Packed fp32 weights `w` (floats):  W_main[128*128] | W_1..W_L [L*128*128] | W_out[128*128]
+ *                                    | b_1..b_L [L*128] | b_out[128] | gamma[128] | beta[128]
+ * all matrices in nn.Linear layout [out][in].  aero_block_prepare turns them into the image
+ * the chosen path reads (SIMT: fp32 + transposes; UMMA: bf16 swizzled shared-memory images).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct aero_block_desc {
+  int32_t dtype;      /* AERO_F32 | AERO_BF16: storage of main/resid/out/P/g_* rows            */
+  int32_t path;       /* AERO_PATH_SIMT | AERO_PATH_UMMA                                       */
+  int32_t L;          /* number of hidden Linear(128,128) layers (config.yaml:48-49 -> 2)      */
+  int32_t act;        /* AERO_ACT_*                                                            */
+  int32_t use_ln;     /* LayerNorm on the block output (mlp.py:34-35)                          */
+  int32_t main_f32;   /* 1: `main` (and g_main) rows are fp32 regardless of dtype (node block:
+                         main = fp32 aggregate)                                                */
+  int32_t has_resid_grad; /* bwd: 1 -> g_main = g_out + g_h0 @ W_main (edge: resid == main)    */
+  int32_t reserved;
+  int64_t rows;       /* E or N                                                                */
+  int64_t n_nodes;    /* N (rows of P, agg)                                                    */
+  int64_t ldp;        /* row stride of P in elements (384)                                     */
+  int64_t poff0, poff1; /* column offsets inside a P row                                       */
+  const void* main;   /* [rows,128]                                                            */
+  const float* main_scale; /* optional [rows] fp32 multiplier on main rows ('mean': 1/deg)     */
+  const void* resid;  /* [rows,128] (edge: == main; node: x)                                   */
+  const void* P;      /* [n_nodes, ldp]                                                        */
+  const int32_t* idx0;/* [rows] or NULL = identity                                             */
+  const int32_t* idx1;/* [rows] or NULL = no second gathered term                              */
+  const int32_t* rowptr; /* receiver CSR [n_nodes+1], needed when agg != NULL                  */
+  const void* prepared;  /* output of aero_block_prepare                                       */
+  void* out;          /* fwd: [rows,128]                                                       */
+  float* agg;         /* fwd: optional [n_nodes,128] fp32                                      */
+  /* backward only */
+  const void* g_out;  /* [rows,128] gradient w.r.t. out                                        */
+  const float* g_agg; /* optional [n_nodes,128] fp32, added as g_agg[idx1[r]] (edge block)     */
+  void* g_main;       /* [rows,128] gradient w.r.t. main (may alias g_out)                     */
+  void* g_h0;         /* [rows,128] gradient w.r.t. the first pre-activation                   */
+  float* g_w;         /* packed like `w`; W_main slot is left untouched (caller: g_h0^T@main)  */
+  void* workspace;
+  size_t workspace_bytes;
+} aero_block_desc;
+
+size_t aero_block_prepared_bytes(int L, int path);
+int aero_block_prepare(const float* w, int L, int path, void* prepared, void* stream);
+size_t aero_block_workspace_bytes(const aero_block_desc* d, int backward);
+int aero_block_fwd(const aero_block_desc* d, void* stream);
+int aero_block_bwd(const aero_block_desc* d, void* stream);
+/* number of kernels the last fwd/bwd call on this thread launched (bench.py gpu_launches) */
+int aero_last_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Bistride pooling index kernels (bit-exact integer work).
+ *
+ * aero_stride_pool_plan: bsms_mgn.py:231-262.  batch must be ascending.  Nodes of each graph
+ * are ordered by pos[:,0] (ties: ascending node id, the CPU torch.argsort result), rank//stride
+ * is the coarse id inside the graph, graphs are concatenated.
+ *   posx        [N] float64 (caller widens pos[:,0] exactly) or NULL -> index order (:245)
+ *   fine_to_coarse [N] int64 out;  coarse_batch [>= ceil-sum] int64 out (caller sizes it N)
+ *   counts      [2] device int64 out: [0] = total coarse nodes
+ * aero_coarsen_edges: bsms_mgn.py:274-288.  key = f2c[row]*max(Nc,1)+f2c[col]; unique sorted
+ * keys -> coarse_edge_index, inverse map, and group lists for the edge-latent mean.
+ *   coarse_edge_index [2,E] int64 out (first Ec columns valid, row stride E)
+ *   inverse     [E] int64 out
+ *   gptr        [E+1] int32 out, glist [E] int32 out: edges of coarse edge u =
+ *               glist[gptr[u]..gptr[u+1]) ascending
+ *   counts      [2] device int64: [0] = Ec
+ * ------------------------------------------------------------------------------------------ */
+size_t aero_stride_pool_workspace_bytes(int64_t N);
+int aero_stride_pool_plan(const int64_t* batch, const double* posx, int64_t N, int64_t stride,
+                          int64_t* fine_to_coarse, int64_t* coarse_batch, int64_t* counts,
+                          void* workspace, size_t workspace_bytes, void* stream);
+size_t aero_coarsen_edges_workspace_bytes(int64_t E);
+int aero_coarsen_edges(const int64_t* edge_index, int64_t E, const int64_t* fine_to_coarse,
+                       int64_t Nc, int64_t* coarse_edge_index, int64_t* inverse,
+                       int32_t* gptr, int32_t* glist, int64_t* counts,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* group lists for a many-to-one int64 map (fine_to_coarse): members of group c ascending */
+size_t aero_group_lists_workspace_bytes(int64_t n);
+int aero_group_lists(const int64_t* group_of, int64_t n, int64_t n_groups,
+                     int32_t* gptr, int32_t* glist, int32_t* group32,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AERO_GNN_H_ */
