@@ -58,6 +58,38 @@ class LaunchCounter:
         cls.total += _l.load().aero_last_launch_count()
 
 
+class _Profile:
+    """Optional CUDA-event timing of the fused block launches on the launching stream (bench.py roofline)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.events = {}
+
+    def reset(self, enabled: bool) -> None:
+        self.enabled = enabled
+        self.events = {}
+
+    def begin(self, kind):
+        if not (self.enabled and kind):
+            return None
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        return (kind, a, b)
+
+    def end(self, tok) -> None:
+        if tok is not None:
+            kind, a, b = tok
+            b.record()
+            self.events.setdefault(kind, []).append((a, b))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return {k: {"count": len(v), "ms_total": sum(a.elapsed_time(b) for a, b in v)} for k, v in self.events.items()}
+
+
+PROFILE = _Profile()
+
+
 # ------------------------------------------------------------------------------------------------
 # graph plan
 # ------------------------------------------------------------------------------------------------
@@ -288,7 +320,7 @@ def _desc(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, main
 
 
 def block_fwd(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, main_scale=None, rowptr=None,
-              want_agg=False):
+              want_agg=False, kind=None):
     """Forward of one fused block; returns (out, agg or None)."""
     _require_cuda(main, resid, P)
     lib = _l.load()
@@ -300,15 +332,17 @@ def block_fwd(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, 
     d.agg = agg.data_ptr() if agg is not None else None
     ws = _workspace(lib.aero_block_workspace_bytes(C.byref(d), 0), P.device)
     d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+    tok = PROFILE.begin(kind)
     with torch.cuda.device(P.device):
         rc = lib.aero_block_fwd(C.byref(d), _stream())
+    PROFILE.end(tok)
     _l.check(rc, "aero_block_fwd")
     LaunchCounter.add()
     return out, agg
 
 
 def block_bwd(prep: PreparedBlock, main, P, idx0, idx1, poff0, poff1, g_out, *, g_agg=None, main_scale=None,
-              has_resid_grad=False, g_main_out: Optional[torch.Tensor] = None):
+              has_resid_grad=False, g_main_out: Optional[torch.Tensor] = None, kind=None):
     """Backward of one fused block; returns (g_main, g_h0, g_w_packed[fp32], W_main slot zero)."""
     _require_cuda(main, P, g_out)
     lib = _l.load()
@@ -325,8 +359,10 @@ def block_bwd(prep: PreparedBlock, main, P, idx0, idx1, poff0, poff1, g_out, *, 
     d.g_w = g_w.data_ptr()
     ws = _workspace(lib.aero_block_workspace_bytes(C.byref(d), 1), P.device)
     d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+    tok = PROFILE.begin(kind)
     with torch.cuda.device(P.device):
         rc = lib.aero_block_bwd(C.byref(d), _stream())
+    PROFILE.end(tok)
     _l.check(rc, "aero_block_bwd")
     LaunchCounter.add()
     return g_main, g_h0, g_w

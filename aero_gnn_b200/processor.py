@@ -78,8 +78,9 @@ class MGNStackFn(torch.autograd.Function):
             pe = ops.PreparedBlock(w_edge.detach(), cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
             pn = ops.PreparedBlock(w_node.detach(), cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
             P = torch.addmm(b_proj.detach(), x, w_proj.detach().t())
-            e_new, agg = ops.block_fwd(pe, e, e, P, plan.src, plan.dst, 0, D, rowptr=plan.rowptr, want_agg=True)
-            x_new, _ = ops.block_fwd(pn, agg, x, P, None, None, 2 * D, 0, main_scale=scale)
+            e_new, agg = ops.block_fwd(pe, e, e, P, plan.src, plan.dst, 0, D, rowptr=plan.rowptr, want_agg=True,
+                                       kind="edge_fwd")
+            x_new, _ = ops.block_fwd(pn, agg, x, P, None, None, 2 * D, 0, main_scale=scale, kind="node_fwd")
             saved += [x, e, agg]
             x, e = x_new, e_new
         ctx.cfg, ctx.plan, ctx.K = cfg, plan, K
@@ -105,12 +106,13 @@ class MGNStackFn(torch.autograd.Function):
             pn = ops.PreparedBlock(w_node, cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
             P = torch.addmm(b_proj, x, w_proj.t())
             # node block: g_agg, gradient of the node pre-activation, MLP weight grads
-            g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale)
+            g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale,
+                                               kind="node_bwd")
             agg_eff = agg if scale is None else agg * scale[:, None]
             g_wn[: D * D] = (g_h0n.float().t() @ agg_eff).reshape(-1)
             # edge block: total gradient of e' = G_e + g_agg[receiver]
             G_e, g_h0e, g_we = ops.block_bwd(pe, e, P, plan.src, plan.dst, 0, D, G_e, g_agg=g_agg,
-                                             has_resid_grad=True, g_main_out=G_e)
+                                             has_resid_grad=True, g_main_out=G_e, kind="edge_bwd")
             g_we[: D * D] = (g_h0e.t() @ e).float().reshape(-1)
             # gradients of the gathered projections: segmented sums by sender and by receiver
             g_ps = ops.segment_reduce(g_h0e, plan.sptr, plan.sperm, plan.N)

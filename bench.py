@@ -1,0 +1,329 @@
+"""bench.py -- MGN-15 processor edges/sec (fwd+bwd) on the synthetic 1M-node / 5.996M-edge wing mesh.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nu 1000 --nv 1000]
+  torchrun ... bench.py --gpus N ...            (one rank per GPU, NCCL; the mesh is partitioned by
+                                                 contiguous receiver-node blocks with a halo exchange per step)
+
+One "step" = one forward + backward of the 15-step MeshGraphNets processor over the whole mesh
+(models/mgn.py:127-128 of the reference; encoders / decoder / loss / optimizer are outside the processor metric).
+`value` = edges / second with the latent inputs resident in HBM; `e2e` = the same metric through the public
+nn.Module API (MeshGraphNet.forward + MSE loss + backward) with the raw features copied from pinned host memory
+and the loss read back every step.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+D = 128
+CFG = dict(processor_size=15, activation_fn="relu", num_hidden_layers_node_processor=2,
+           num_hidden_layers_edge_processor=2, hidden_dim_processor=128, num_hidden_layers_node_encoder=2,
+           hidden_dim_node_encoder=128, num_hidden_layers_edge_encoder=2, hidden_dim_edge_encoder=128,
+           aggregation="add", hidden_dim_decoder=128, num_hidden_layers_decoder=2, dropout=0.0,
+           do_concat_trick=True)   # config.yaml:40-51
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return j["hbm_gbs"], j.get("bf16_tflops_sustained", j["bf16_tflops"]), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+def alg_bytes_step(E, N, b, K=15):
+    """fwd+bwd bytes of K processor steps."""
+    return K * ((5 * E + 5 * N) * D * b + 8 * E + 8 * (N + 1))
+
+
+def kernel_alg_bytes(kind, E, N, b):
+    """Algorithmic bytes of one launch of a fused block kernel (DESIGN.md 'Roofline accounting')."""
+    return {"edge_fwd": E * (2 * D * b + 8) + 4 * (N + 1),      # read e, write e', src/dst ids, rowptr
+            "edge_bwd": E * (3 * D * b + 8),                    # read e, read de', write de, ids
+            "node_fwd": N * 2 * D * b, "node_bwd": N * 3 * D * b}[kind]
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_port_step(nu, nv, threads):
+    """The reference algorithm (oracle port, torch CPU fp32 + autograd) on a bounded wing sub-mesh; returns
+    (edges_per_second, sample description).  The only place besides tests/ and smoke() that runs oracle/."""
+    from aero_gnn_b200.meshes import wing_surface_mesh
+    from oracle import mgn_oracle as O
+    import aero_gnn_b200.models as M
+    torch.set_num_threads(threads)
+    mesh = wing_surface_mesh(nu, nv)
+    torch.manual_seed(0)
+    net = M.MeshGraphNet(6, 4, 5, **CFG)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(1234)
+    x0 = torch.randn(mesh.num_nodes, D, generator=g).requires_grad_(True)
+    e0 = torch.randn(mesh.num_edges, D, generator=g).requires_grad_(True)
+
+    def step():
+        x, e = x0, e0
+        for i in range(CFG["processor_size"]):
+            x, e = O.mgn_layer(sd, f"layers.{i}.", x, e, mesh.edge_index, "add")
+        params = [v for k, v in sd.items() if k.startswith("layers.")]
+        torch.autograd.grad(x.sum() + e.sum(), [x0, e0] + params)
+
+    return step, mesh.num_edges, f"wing {nu}x{nv}: N={mesh.num_nodes} E={mesh.num_edges}, fp32, torch CPU autograd"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    nu, nv = 120, 60
+    step, E, desc = cpu_port_step(nu, nv, threads)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = E / dt
+    line = {"impl": "reference", "metric": "MGN-15 processor edges/sec (fwd+bwd)", "value": val, "unit": "edges/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "MGN-15 processor fwd+bwd, 1M-node/5.996M-edge wing mesh (C5); CPU arm timed on "
+                                   "a bounded sub-mesh of the same generator", "sample": desc},
+            "cpu_baseline": {"value": val, "unit": "edges/s", "cores": threads, "kind": "port", "sample": desc},
+            "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nu", type=int, default=1000)
+    ap.add_argument("--nv", type=int, default=1000)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from aero_gnn_b200 import lib, ops
+    import aero_gnn_b200.models as M
+    from aero_gnn_b200.meshes import wing_surface_mesh
+    from aero_gnn_b200.models._common import run_layers
+
+    lib.load()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    b = 2 if dt == torch.bfloat16 else 4
+
+    mesh = wing_surface_mesh(args.nu, args.nv)
+    N, E = mesh.num_nodes, mesh.num_edges
+    torch.manual_seed(0)
+    net = M.MeshGraphNet(6, 4, 5, **CFG).to(dev).to(dt)
+
+    # ---- device-resident processor benchmark ----------------------------------------------------
+    g = torch.Generator().manual_seed(1234)
+    if world == 1:
+        plan = ops.PLAN_CACHE.get(mesh.edge_index.to(dev), N)
+        x0 = torch.randn(N, D, generator=g).to(dev, dt).requires_grad_(True)
+        e0 = torch.randn(E, D, generator=g).to(dev, dt).requires_grad_(True)
+        gx = torch.ones(N, D, device=dev, dtype=dt)
+
+        def proc_step():
+            for p in net.layers.parameters():
+                p.grad = None
+            x0.grad = e0.grad = None
+            x, e = run_layers(net.layers, plan, x0, e0)
+            torch.autograd.backward([x], [gx])
+        parallelism = "single"
+    else:
+        from aero_gnn_b200.partition import PartitionedProcessor
+        pp = PartitionedProcessor(mesh.edge_index, N, rank, world, dev)
+        x0 = torch.randn(N, D, generator=g)[pp.lo:pp.hi].to(dev, dt).requires_grad_(True)
+        e0 = torch.randn(E, D, generator=g)[pp.edge_ids_cpu].to(dev, dt).requires_grad_(True)
+        gx = torch.ones(pp.n_own, D, device=dev, dtype=dt)
+
+        def proc_step():
+            for p in net.layers.parameters():
+                p.grad = None
+            x0.grad = e0.grad = None
+            x, e = pp.run(net.layers, x0, e0)
+            torch.autograd.backward([x], [gx])
+            pp.allreduce_grads(net.layers.parameters())
+        parallelism = f"receiver-block partition x{world} + halo exchange"
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        proc_step()
+    sync_all()
+    ops.PROFILE.reset(enabled=True)
+    l0 = ops.LaunchCounter.total
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        proc_step()
+    ev1.record()
+    sync_all()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches = ops.LaunchCounter.total - l0
+    clocks = sampler.stop() if rank == 0 else None
+    prof = ops.PROFILE.summary()
+    ops.PROFILE.reset(enabled=False)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = E / (ms * 1e-3)
+
+    # ---- end-to-end through the public API: pinned host -> device, model fwd, loss, bwd, loss readback ----
+    e2e = None
+    if not args.no_e2e and world == 1:
+        host = [mesh.node_attr.pin_memory(), mesh.edge_attr.pin_memory(), mesh.edge_index.pin_memory(),
+                mesh.target.pin_memory()]
+        h2d = sum(t.numel() * t.element_size() for t in host)
+        lossf = torch.nn.MSELoss()
+
+        def e2e_step():
+            na, ea, ei, tg = (t.to(dev, non_blocking=True) for t in host)
+            net.zero_grad(set_to_none=True)
+            pred = net(na.to(dt), ea.to(dt), ei)
+            loss = lossf(pred.float(), tg)
+            loss.backward()
+            return float(loss.item())
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        torch.cuda.synchronize()
+        n_e2e = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / n_e2e
+        e2e = {"value": E / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+               "ms_per_step": e2e_s * 1e3, "api": "MeshGraphNet.forward + MSELoss + backward (encoders/decoder included)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm, tc, which = peaks()
+    # dominant kernel = the fused block launch with the largest share of the step
+    dom = max(prof, key=lambda k: prof[k]["ms_total"]) if prof else None
+    roof = None
+    if dom:
+        n_rows_E = E if world == 1 else pp.E_loc
+        n_rows_N = N if world == 1 else pp.n_own
+        ab = kernel_alg_bytes(dom, n_rows_E, n_rows_N, b)
+        avg_ms = prof[dom]["ms_total"] / max(prof[dom]["count"], 1)
+        ach = ab / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                "peak_source": which, "traffic": None, "avg_ms_per_launch": avg_ms,
+                "share_of_step": prof[dom]["ms_total"] / (ms * args.steps),
+                "kernels": {k: {"avg_ms": v["ms_total"] / max(v["count"], 1), "share": v["ms_total"] / (ms * args.steps)}
+                            for k, v in prof.items()},
+                "step_alg_gbytes": alg_bytes_step(E, N, b) / 1e9,
+                "step_frac_hbm": alg_bytes_step(E, N, b) / world / (ms * 1e-3) / 1e9 / hbm}
+    cpu = None
+    if not args.no_cpu and world == 1:
+        threads = os.cpu_count() or 1
+        step, Es, desc = cpu_port_step(120, 60, threads)
+        step()
+        t0 = time.perf_counter()
+        step()
+        cs = time.perf_counter() - t0
+        cpu = {"value": Es / cs, "unit": "edges/s", "cores": threads, "kind": "port", "sample": desc}
+
+    line = {"metric": "MGN-15 processor edges/sec (fwd+bwd)", "value": value, "unit": "edges/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "edge_steps_per_s": 15 * value,
+            "config": {"workload": f"MGN-15 processor fwd+bwd on the synthetic 3-D wing surface mesh (C5): "
+                                   f"N={N} E={E}, latent 128, L=2, sum-trick edge block, aggregation add",
+                       "parallelism": parallelism, "l2": "inputs (>1.7 GB of latents per step) are larger than L2",
+                       "path": "umma" if lib.load().aero_has_umma() and dt == torch.bfloat16 else "simt"},
+            "clocks": clocks, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
