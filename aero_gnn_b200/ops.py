@@ -266,11 +266,16 @@ def packed_floats(L: int) -> int:
     return (L + 2) * D * D + (L + 3) * D
 
 
-def choose_path(dtype: torch.dtype, act: str) -> int:
-    """bf16 rows run on tcgen05 when the library has it; fp32 rows run the exact CUDA-core path."""
+UMMA_MAX_L = 2
+
+
+def choose_path(dtype: torch.dtype, act: str, L: int = 0, backward: bool = False) -> int:
+    """bf16 rows run on tcgen05 when the library has the kernel; fp32 rows run the exact CUDA-core path."""
     if os.environ.get("AERO_FORCE_SIMT", "0") == "1":
         return _l.AERO_PATH_SIMT
-    if dtype == torch.bfloat16 and act == "relu" and _l.load().aero_has_umma():
+    lib = _l.load()
+    have = lib.aero_has_umma_bwd() if backward else lib.aero_has_umma()
+    if dtype == torch.bfloat16 and L <= UMMA_MAX_L and have:
         return _l.AERO_PATH_UMMA
     return _l.AERO_PATH_SIMT
 

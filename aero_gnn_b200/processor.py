@@ -69,8 +69,8 @@ class MGNStackFn(torch.autograd.Function):
         K = len(flat) // 4
         x = x.contiguous()
         e = e.contiguous()
-        path_e = ops.choose_path(x.dtype, cfg.act_edge)
-        path_n = ops.choose_path(x.dtype, cfg.act_node)
+        path_e = ops.choose_path(x.dtype, cfg.act_edge, cfg.L_edge)
+        path_n = ops.choose_path(x.dtype, cfg.act_node, cfg.L_node)
         scale = plan.inv_deg if cfg.mean else None
         saved = []
         for k in range(K):
@@ -84,7 +84,8 @@ class MGNStackFn(torch.autograd.Function):
             saved += [x, e, agg]
             x, e = x_new, e_new
         ctx.cfg, ctx.plan, ctx.K = cfg, plan, K
-        ctx.paths = (path_e, path_n)
+        ctx.paths = (ops.choose_path(x.dtype, cfg.act_edge, cfg.L_edge, backward=True),
+                     ops.choose_path(x.dtype, cfg.act_node, cfg.L_node, backward=True))
         ctx.save_for_backward(*saved, *flat)
         return x, e
 
@@ -167,8 +168,9 @@ class SingleBlockFn(torch.autograd.Function):
         if x.size(1) != D or e.size(1) != D:
             raise RuntimeError(f"the fused sm_100a path supports latent width {D} only")
         e, x = e.contiguous(), x.contiguous()
-        path = ops.choose_path(x.dtype, act)
+        path = ops.choose_path(x.dtype, act, L)
         prep = ops.PreparedBlock(w.detach(), L, path, act, use_ln)
+        path = ops.choose_path(x.dtype, act, L, backward=True)
         P = torch.addmm(b_proj.detach(), x, w_proj.detach().t())
         scale = plan.inv_deg if (mean and mode == "node") else None
         if mode == "edge":

@@ -55,8 +55,14 @@ extern "C" {
 
 const char* aero_last_error(void);
 int aero_version(void);
-/* 1 when the library was compiled with the tcgen05 (UMMA) kernels */
+/* 1 when the library was compiled with the tcgen05 (UMMA) forward kernels / backward kernels */
 int aero_has_umma(void);
+int aero_has_umma_bwd(void);
+/* tcgen05 primitive self-test: one 128x128x128 bf16 GEMM, fp32 result c[128][128] (row-major inputs).
+ *   mode 0: c = a  * b^T   (both operands K-major: forward Linear)
+ *   mode 1: c = a  * b     (b MN-major: data gradient)
+ *   mode 2: c = a^T * b    (both MN-major: weight gradient) */
+int aero_umma_selftest(const void* a_bf16, const void* b_bf16, float* c, int mode, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Graph plan: receiver-CSR + sender-CSR, built once per mesh.
@@ -145,7 +151,7 @@ typedef struct aero_block_desc {
   int64_t poff0, poff1; /* column offsets inside a P row                                       */
   const void* main;   /* [rows,128]                                                            */
   const float* main_scale; /* optional [rows] fp32 multiplier on main rows ('mean': 1/deg)     */
-  const void* resid;  /* [rows,128] (edge: == main; node: x)                                   */
+  const void* resid;  /* [rows,128] (edge: == main; node: x); NULL = no residual (standalone block) */
   const void* P;      /* [n_nodes, ldp]                                                        */
   const int32_t* idx0;/* [rows] or NULL = identity                                             */
   const int32_t* idx1;/* [rows] or NULL = no second gathered term                              */
