@@ -83,3 +83,81 @@ def test_umma_forward_is_deterministic():
     a = _run_layer(layer, x, ea, ei, False)
     b = _run_layer(layer, x, ea, ei, False)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def _grads(layer, x, e, ei, probe, force_simt):
+    old = os.environ.get("AERO_FORCE_SIMT")
+    os.environ["AERO_FORCE_SIMT"] = "1" if force_simt else "0"
+    try:
+        for p in layer.parameters():
+            p.grad = None
+        xg, eg = x.clone().requires_grad_(True), e.clone().requires_grad_(True)
+        xo, eo = layer(xg, eg, ei)
+        (torch.cat([xo, eo], 0).float() * probe).sum().backward()
+        return xg.grad.float(), eg.grad.float(), {n: p.grad.float().clone() for n, p in layer.named_parameters()}
+    finally:
+        if old is None:
+            os.environ.pop("AERO_FORCE_SIMT", None)
+        else:
+            os.environ["AERO_FORCE_SIMT"] = old
+
+
+@pytest.mark.parametrize("name", ["layer_sum_L2_add", "layer_cat_L1_mean"])
+@pytest.mark.parametrize("n,e", [(37, 301), (300, 2111), (10, 700), (5000, 29600)])
+def test_umma_backward_matches_simt_and_oracle(name, n, e):
+    import aero_gnn_b200.models as M
+    from aero_gnn_b200 import lib as L
+    assert L.load().aero_has_umma_bwd() == 1
+    g = load_golden(name)
+    layer = M.MeshGraphNetLayer(128, 128, 128, **g["kwargs"])
+    layer.load_state_dict(g["state"])
+    layer = layer.to(DEV).to(torch.bfloat16)
+    gen = torch.Generator().manual_seed(n + e)
+    x = torch.randn(n, 128, generator=gen).to(torch.bfloat16)
+    ea = torch.randn(e, 128, generator=gen).to(torch.bfloat16)
+    ei = torch.randint(0, n, (2, e), generator=gen)
+    probe = torch.randn(n + e, 128, generator=gen)
+    gs = _grads(layer, x.to(DEV), ea.to(DEV), ei.to(DEV), probe.to(DEV), True)
+    gu = _grads(layer, x.to(DEV), ea.to(DEV), ei.to(DEV), probe.to(DEV), False)
+    # Truth: fp32 oracle autograd on the bf16-held parameters / inputs.  Yardstick: the reference's own bf16 mode
+    # (train.py:30-33 = pure bf16 tensors and autograd), restated by running the oracle in bf16 on the CPU.  The
+    # tensor-core path must be at least as close to the fp32 truth as that (25 % slack), or within 1e-2.
+    def oracle(dt):
+        sd = {k: v.to(torch.bfloat16).to(dt).requires_grad_(True) for k, v in g["state"].items()}
+        xr, er = x.to(dt).requires_grad_(True), ea.to(dt).requires_grad_(True)
+        xo, eo = O.mgn_layer(sd, "", xr, er, ei, g["kwargs"]["aggregation"])
+        names = list(sd)
+        gr = torch.autograd.grad((torch.cat([xo, eo], 0).float() * probe).sum(), [xr, er] + [sd[k] for k in names])
+        return names, [t.float() for t in gr]
+    names, ref = oracle(torch.float32)
+    _, ref16 = oracle(torch.bfloat16)
+
+    def ok(mine, truth, yard, what):
+        err, bar = rel_l2(mine, truth), max(1e-2, 1.25 * rel_l2(yard, truth))
+        assert err <= bar, (what, err, bar)
+        return err / bar
+    worst = max(ok(gu[0], ref[0], ref16[0], "g_x"), ok(gu[1], ref[1], ref16[1], "g_e"))
+    for k, gr, g16 in zip(names, ref[2:], ref16[2:]):
+        worst = max(worst, ok(gu[2][k], gr, g16, k))
+    # and it must stay close to the fp32-math kernels on the same bf16 data
+    assert rel_l2(gu[0], gs[0]) < 6e-2 and rel_l2(gu[1], gs[1]) < 6e-2
+    print("umma bwd worst error / allowance:", worst)
+
+
+def test_umma_backward_is_deterministic():
+    import aero_gnn_b200.models as M
+    g = load_golden("layer_sum_L2_add")
+    layer = M.MeshGraphNetLayer(128, 128, 128, **g["kwargs"])
+    layer.load_state_dict(g["state"])
+    layer = layer.to(DEV).to(torch.bfloat16)
+    gen = torch.Generator().manual_seed(3)
+    n, e = 30000, 200000
+    x = torch.randn(n, 128, generator=gen).to(DEV, torch.bfloat16)
+    ea = torch.randn(e, 128, generator=gen).to(DEV, torch.bfloat16)
+    ei = torch.randint(0, n, (2, e), generator=gen).to(DEV)
+    probe = torch.randn(n + e, 128, generator=gen).to(DEV)
+    a = _grads(layer, x, ea, ei, probe, False)
+    b = _grads(layer, x, ea, ei, probe, False)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    for k in a[2]:
+        assert torch.equal(a[2][k], b[2][k]), k
