@@ -1,21 +1,27 @@
-// block_umma.cu -- fused MGN block on the 5th-generation tensor cores (tcgen05.mma, bf16 operands, fp32
-// accumulators in TMEM).  bf16 storage path of aero_block_fwd / aero_block_bwd.
+// block_umma.cu -- fused MGN block, forward, on the 5th-generation tensor cores (tcgen05.mma, bf16 operands, fp32
+// accumulators in TMEM).  bf16 storage path of aero_block_fwd.
 //
-// Forward kernel (one persistent CTA per SM, two independent 128-thread warpgroups per CTA):
-//   * all (L+2) weight matrices of the block live in shared memory for the whole kernel as bf16 SWIZZLE_128B
-//     row tiles (umma.cuh), loaded once per CTA;
-//   * a warpgroup owns a 128-row tile: it stages the rows into its activation tile, one elected thread issues the
-//     8 tcgen05.mma (K = 16 each) of a 128x128x128 GEMM into the warpgroup's 128 TMEM columns and commits to an
-//     mbarrier; the 128 threads then read the accumulator with tcgen05.ld (thread = row), apply the epilogue
-//     (gathered pre-projections / bias, activation, bf16 pack) and write the next GEMM's A operand back into the
-//     same activation tile;
-//   * the last epilogue keeps the whole row in registers: bias, LayerNorm (fp32 statistics), residual, bf16 pack;
-//     the output tile goes through shared memory so the global store is coalesced and the receiver sums
-//     (segmented, CSR order, fp32) read it column-wise;
-//   * while one warpgroup is in an epilogue the other one's MMAs keep the tensor pipe busy.
+// One persistent CTA per SM, 512 threads = two independent 256-thread tile groups.  A group owns one 128-row tile:
+//   * all (L+2) weight matrices of the block stay in shared memory for the whole kernel as bf16 SWIZZLE_128B row
+//     tiles (umma.cuh), loaded once per CTA;
+//   * the group stages its rows into its activation tile; one elected thread issues the 8 tcgen05.mma (K = 16 each)
+//     of a 128x128x128 GEMM into the group's 128 TMEM columns and commits to an mbarrier;
+//   * epilogue: thread = (row, 64-column half) -- warp w reads TMEM lanes 32*(w%4).., columns 64*(w/4).. with
+//     tcgen05.ld, adds the gathered pre-projections (layer 0) or the bias, applies the activation, packs to bf16
+//     and writes the next GEMM's A operand into the same activation tile (the MMA that read it has completed);
+//   * last epilogue: bias + LayerNorm (fp32 row statistics, the two column halves exchange partial sums through
+//     shared memory) + residual, bf16 pack into the tile; the tile is then stored to HBM with coalesced 16-byte
+//     chunks and reduced per receiver (one warp per CSR segment, fp32, fixed order) into agg;
+//   * while one group is in an epilogue, the other group's MMAs run: 16 resident warps per SM keep both the
+//     tensor pipe and the LSU/ALU pipes busy.  Epilogue loops are chunked (32 columns) and not unrolled across
+//     chunks so the instruction footprint stays inside the instruction cache.
 #include "umma_block.cuh"
 
 namespace aero {
+
+constexpr int FWD_GROUPS = 2;
+constexpr int FWD_GT = 256;                       // threads per tile group
+constexpr int FWD_THREADS = FWD_GROUPS * FWD_GT;
 
 // ---- weight images ------------------------------------------------------------------------------
 __global__ void umma_prepare_kernel(const float* __restrict__ w, int L, uint8_t* __restrict__ prep) {
@@ -40,68 +46,99 @@ __global__ void umma_prepare_kernel(const float* __restrict__ w, int L, uint8_t*
 // =============================================================================================
 // forward
 // =============================================================================================
-template <int NWG>
-__global__ void __launch_bounds__(NWG * 128, 1) umma_block_fwd_kernel(UmmaArgs a) {
+__global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   const int L = a.L;
   uint8_t* Wimg = smem;
   uint8_t* Abuf = Wimg + (size_t)(L + 2) * TILE_BYTES;
-  float* vec = reinterpret_cast<float*>(Abuf + (size_t)NWG * TILE_BYTES);
-  int* sidx = reinterpret_cast<int*>(vec + (L + 3) * 128);
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(sidx + NWG * 256);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + NWG);
+  float* vec = reinterpret_cast<float*>(Abuf + (size_t)FWD_GROUPS * TILE_BYTES);
+  int* sidx = reinterpret_cast<int*>(vec + (L + 3) * 128);                     // [group][2][128]
+  float2* red = reinterpret_cast<float2*>(sidx + FWD_GROUPS * 256);            // [group][2][128] LN partials
+  uint32_t* segmask = reinterpret_cast<uint32_t*>(red + FWD_GROUPS * 256);     // [group][8]: 4 masks + 2 flags
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(segmask + FWD_GROUPS * 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + FWD_GROUPS);
 
-  const int tid = threadIdx.x, wg = tid >> 7, wt = tid & 127, lane = tid & 31, q = (tid >> 5) & 3;
+  const int tid = threadIdx.x, grp = tid / FWD_GT, gt = tid % FWD_GT, lane = tid & 31;
+  const int gw = gt >> 5;            // warp inside the group, 0..7
+  const int q = gw & 3;              // TMEM lane quarter (== warp id % 4)
+  const int hf = gw >> 2;            // column half
+  const int row = q * 32 + lane;
   // weights + vectors, once per CTA
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.prep);
     uint4* dst = reinterpret_cast<uint4*>(Wimg);
     const int n16 = (L + 2) * (TILE_BYTES / 16);
-    for (int i = tid; i < n16; i += NWG * 128) dst[i] = src[i];
+    for (int i = tid; i < n16; i += FWD_THREADS) dst[i] = src[i];
     const float* vs = reinterpret_cast<const float*>(a.prep + (size_t)(L + 2) * TILE_BYTES);
-    for (int i = tid; i < (L + 3) * 128; i += NWG * 128) vec[i] = vs[i];
+    for (int i = tid; i < (L + 3) * 128; i += FWD_THREADS) vec[i] = vs[i];
   }
   if (tid == 0) {
-    for (int w = 0; w < NWG; ++w) mbar_init(smem_u32(&mbar[w]), 1);
+    for (int w = 0; w < FWD_GROUPS; ++w) mbar_init(smem_u32(&mbar[w]), 1);
     fence_mbar_init();
   }
-  if (tid < 32) tmem_alloc<NWG * 128>(tmem_slot);
+  if (tid < 32) tmem_alloc<FWD_GROUPS * 128>(tmem_slot);
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tacc = tmem_base + (uint32_t)wg * 128u;
-  const uint32_t tlane = tacc + ((uint32_t)(q * 32) << 16);   // this warp's lane quarter
-  uint8_t* A = Abuf + (size_t)wg * TILE_BYTES;
+  const uint32_t tacc = tmem_base + (uint32_t)grp * 128u;
+  const uint32_t tlane = tacc + ((uint32_t)(q * 32) << 16);
+  uint8_t* A = Abuf + (size_t)grp * TILE_BYTES;
   const uint32_t a_s = smem_u32(A);
   const uint32_t w_s = smem_u32(Wimg);
-  const uint32_t bar_s = smem_u32(&mbar[wg]);
-  int* sidx0 = sidx + wg * 256;
+  const uint32_t bar_s = smem_u32(&mbar[grp]);
+  int* sidx0 = sidx + grp * 256;
   int* sidx1 = sidx0 + 128;
+  float2* gred = red + grp * 256;
+  uint32_t* gmask = segmask + grp * 8;
+  const int bar_id = 1 + grp;
   uint32_t phase = 0;
   const int act = a.act;
-  const int row = wt;   // epilogue: thread = tile row = TMEM lane
 
   const int64_t tiles = (a.rows + 127) / 128;
-  for (int64_t tile = (int64_t)blockIdx.x * NWG + wg; tile < tiles; tile += (int64_t)gridDim.x * NWG) {
+  for (int64_t tile = (int64_t)blockIdx.x * FWD_GROUPS + grp; tile < tiles; tile += (int64_t)gridDim.x * FWD_GROUPS) {
     const int64_t row0 = tile * 128;
     const int nrows = (int)((a.rows - row0) < 128 ? (a.rows - row0) : 128);
-    wg_sync(1 + wg);   // previous tile of this warpgroup fully consumed
-    if (a.main_f32) stage_rows<true>(A, a.main, a.main_scale, row0, nrows, wt);
-    else stage_rows<false>(A, a.main, nullptr, row0, nrows, wt);
-    {
-      int64_t r = row0 + wt;
-      bool ok = wt < nrows;
-      sidx0[wt] = ok ? (a.idx0 ? a.idx0[r] : (int)r) : 0;
-      sidx1[wt] = ok ? (a.idx1 ? a.idx1[r] : -1) : -1;
+    named_sync(bar_id, FWD_GT);   // previous tile of this group fully consumed
+    if (a.main_f32) stage_rows<true, FWD_GT>(A, a.main, a.main_scale, row0, nrows, gt);
+    else stage_rows<false, FWD_GT>(A, a.main, nullptr, row0, nrows, gt);
+    if (gt < 128) {
+      int64_t r = row0 + gt;
+      bool ok = gt < nrows;
+      int i0 = ok ? (a.idx0 ? a.idx0[r] : (int)r) : 0;
+      int i1 = ok ? (a.idx1 ? a.idx1[r] : -1) : -1;
+      sidx0[gt] = i0;
+      sidx1[gt] = i1;
+      if (a.agg) {
+        // receiver-segment heads of this tile (rows are in CSR order) + completeness of the two boundary segments
+        int prev = __shfl_up_sync(0xffffffffu, i1, 1);
+        if (lane == 0) prev = (gt == 0 || !ok) ? -2 : a.idx1[r - 1];
+        uint32_t m = __ballot_sync(0xffffffffu, ok && (gt == 0 || i1 != prev));
+        if (lane == 0) gmask[gw] = m;
+        if (gt == 0) gmask[4] = (a.rowptr[i1] < row0) ? 1u : 0u;                                 // head started earlier
+        if (gt == nrows - 1) gmask[5] = ((int64_t)a.rowptr[i1 + 1] > row0 + nrows) ? 1u : 0u;    // tail continues
+      }
     }
     fence_async_smem();
-    wg_sync(1 + wg);
+    named_sync(bar_id, FWD_GT);
+    // pull this group's next tile into L2 while the current one computes
+    {
+      const int64_t r = (tile + (int64_t)gridDim.x * FWD_GROUPS) * 128 + (gt >> 1);
+      if (r < a.rows) {
+        if (a.main_f32) {
+          const float* p = reinterpret_cast<const float*>(a.main) + r * 128 + (gt & 1) * 64;
+          prefetch_l2(p);
+          prefetch_l2(p + 32);
+        } else {
+          prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(a.main) + r * 128 + (gt & 1) * 64);
+        }
+      }
+    }
 
     for (int layer = 0; layer <= L + 1; ++layer) {
-      if (wt == 0) {
+      if (gt == 0) {
         fence_after_sync();
         issue_gemm(tacc, a_s, false, w_s + (uint32_t)layer * TILE_BYTES, false, false);
         mma_commit(bar_s);
@@ -111,117 +148,109 @@ __global__ void __launch_bounds__(NWG * 128, 1) umma_block_fwd_kernel(UmmaArgs a
       fence_after_sync();
 
       if (layer <= L) {
-        // hidden epilogue: (+ gathered pre-projections | + bias), activation, bf16, back into the A tile
-        const bool valid = row < nrows;
         const __nv_bfloat16* p0 = nullptr;
         const __nv_bfloat16* p1 = nullptr;
-        if (layer == 0 && valid) {
+        if (layer == 0 && row < nrows) {
           p0 = a.P + (int64_t)sidx0[row] * a.ldp + a.poff0;
           if (sidx1[row] >= 0) p1 = a.P + (int64_t)sidx1[row] * a.ldp + a.poff1;
         }
         const float* bias = layer > 0 ? vec + (layer - 1) * 128 : nullptr;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint4 g0[4], g1[4];
-          if (layer == 0) {
+        for (int cc = 0; cc < 2; ++cc) hidden_epilogue_chunk(tlane, hf * 2 + cc, p0, p1, bias, act, A, row);
+        fence_before_sync();
+        fence_async_smem();
+        named_sync(bar_id, FWD_GT);
+      } else {
+        // ---- output epilogue: bias, LayerNorm, residual ----
+        const float* bo = vec + L * 128;
+        float mean = 0.f, rstd = 1.f;
+        if (a.use_ln) {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll 1
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = hf * 2 + cc;
+            float v[32];
+            tmem_ld32(tlane + (uint32_t)(c * 32), v);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              g0[j] = p0 ? *reinterpret_cast<const uint4*>(p0 + c * 32 + j * 8) : make_uint4(0u, 0u, 0u, 0u);
-              g1[j] = p1 ? *reinterpret_cast<const uint4*>(p1 + c * 32 + j * 8) : make_uint4(0u, 0u, 0u, 0u);
+            for (int j = 0; j < 8; ++j) {
+              float4 b4 = *reinterpret_cast<const float4*>(bo + c * 32 + 4 * j);
+              float y0 = v[4 * j] + b4.x, y1 = v[4 * j + 1] + b4.y, y2 = v[4 * j + 2] + b4.z, y3 = v[4 * j + 3] + b4.w;
+              s0 += y0; s1 += y1; s2 += y2; s3 += y3;
+              t0 = fmaf(y0, y0, t0); t1 = fmaf(y1, y1, t1); t2 = fmaf(y2, y2, t2); t3 = fmaf(y3, y3, t3);
             }
+          }
+          gred[hf * 128 + row] = make_float2((s0 + s1) + (s2 + s3), (t0 + t1) + (t2 + t3));
+          named_sync(bar_id, FWD_GT);
+          float2 pa = gred[row], pb = gred[128 + row];
+          mean = (pa.x + pb.x) * (1.f / 128.f);
+          float var = fmaxf((pa.y + pb.y) * (1.f / 128.f) - mean * mean, 0.f);
+          rstd = rsqrtf(var + 1e-5f);
+        }
+        const float* gam = vec + (L + 1) * 128;
+        const float* bet = vec + (L + 2) * 128;
+        const bool valid = row < nrows;
+        const __nv_bfloat16* rp = (a.resid && valid) ? a.resid + (row0 + row) * 128 : nullptr;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = hf * 2 + cc;
+          uint4 r4[4];
+          if (rp) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r4[j] = *reinterpret_cast<const uint4*>(rp + c * 32 + j * 8);
           }
           float v[32];
           tmem_ld32(tlane + (uint32_t)(c * 32), v);
-          if (layer == 0) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              add_bf16x8(v + 8 * j, g0[j]);
-              add_bf16x8(v + 8 * j, g1[j]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += bias[c * 32 + j];
+          for (int j = 0; j < 8; ++j) {
+            float4 b4 = *reinterpret_cast<const float4*>(bo + c * 32 + 4 * j);
+            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
           }
+          if (a.use_ln) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = valid ? relu_or_act(v[j], act) : 0.f;
+            for (int j = 0; j < 8; ++j) {
+              float4 g4 = *reinterpret_cast<const float4*>(gam + c * 32 + 4 * j);
+              float4 e4 = *reinterpret_cast<const float4*>(bet + c * 32 + 4 * j);
+              v[4 * j] = fmaf((v[4 * j] - mean) * rstd, g4.x, e4.x);
+              v[4 * j + 1] = fmaf((v[4 * j + 1] - mean) * rstd, g4.y, e4.y);
+              v[4 * j + 2] = fmaf((v[4 * j + 2] - mean) * rstd, g4.z, e4.z);
+              v[4 * j + 3] = fmaf((v[4 * j + 3] - mean) * rstd, g4.w, e4.w);
+            }
+          }
+          if (rp) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) add_bf16x8(v + 8 * j, r4[j]);
+          }
           store_row32(A, row, c, v);
         }
         fence_before_sync();
-        fence_async_smem();
-        wg_sync(1 + wg);
-      } else {
-        // output epilogue: bias, LayerNorm, residual; whole row in registers
-        float v[128];
-        const float* bo = vec + L * 128;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float t[32];
-          tmem_ld32(tlane + (uint32_t)(c * 32), t);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[c * 32 + j] = t[j] + bo[c * 32 + j];
-        }
-        fence_before_sync();
-        if (a.use_ln) {
-          float s = 0.f;
-#pragma unroll
-          for (int j = 0; j < 128; ++j) s += v[j];
-          const float mean = s * (1.f / 128.f);
-          float ss = 0.f;
-#pragma unroll
-          for (int j = 0; j < 128; ++j) {
-            float d = v[j] - mean;
-            ss = fmaf(d, d, ss);
-          }
-          const float rstd = rsqrtf(ss * (1.f / 128.f) + 1e-5f);
-          const float* gam = vec + (L + 1) * 128;
-          const float* bet = vec + (L + 2) * 128;
-#pragma unroll
-          for (int j = 0; j < 128; ++j) v[j] = fmaf((v[j] - mean) * rstd, gam[j], bet[j]);
-        }
-        const bool valid = row < nrows;
-        if (a.resid && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(a.resid + (row0 + row) * 128);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) add_bf16x8(v + 8 * j, rp[j]);
-        }
-        if (!valid) {
-#pragma unroll
-          for (int j = 0; j < 128; ++j) v[j] = 0.f;
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) store_row32(A, row, c, v + 32 * c);
-        wg_sync(1 + wg);
+        named_sync(bar_id, FWD_GT);
         // coalesced store of the output tile
-        {
-          const int chunk = wt & 15;
-#pragma unroll 4
-          for (int i = 0; i < 16; ++i) {
-            int r = (wt >> 4) + i * 8;
-            if (r < nrows)
-              *reinterpret_cast<uint4*>(a.out + (row0 + r) * 128 + chunk * 8) =
-                  *reinterpret_cast<const uint4*>(A + tile_chunk_off(r, chunk));
-          }
-        }
+        unstage_rows<FWD_GT>(A, a.out, row0, nrows, gt);
         if (a.agg) {
-          // receiver sums over the bf16-rounded rows: thread = column, CSR order
-          const int c = wt;
-          const uint8_t* colp = A + (c >> 6) * PANEL_BYTES + (c & 7) * 2;
-          const int cc = (c >> 3) & 7;
-          const int64_t tile_end = row0 + nrows;
-          int r = 0;
-          while (r < nrows) {
-            int n = sidx1[r];
-            int b = a.rowptr[n], e = a.rowptr[n + 1];
-            int re = (int)(((int64_t)e < tile_end ? (int64_t)e : tile_end) - row0);
-            float s = 0.f;
-            for (int t = r; t < re; ++t) {
-              uint16_t h = *reinterpret_cast<const uint16_t*>(colp + t * 128 + ((cc ^ (t & 7)) << 4));
-              s += __uint_as_float((uint32_t)h << 16);
+          // receiver sums over the bf16-rounded rows: one warp per CSR segment, lane = 4 columns, rows in order
+          const uint8_t* base = A + (lane >> 4) * PANEL_BYTES + (lane & 1) * 8;
+          const int ch = (lane >> 1) & 7;
+          const bool head_open = gmask[4] != 0, tail_open = gmask[5] != 0;
+          int k = 0, prev_start = -1;
+          for (int wd = 0; wd <= 4; ++wd) {
+            uint32_t m = wd < 4 ? gmask[wd] : 1u;   // sentinel closes the last segment
+            while (m) {
+              int start = wd < 4 ? wd * 32 + (__ffs(m) - 1) : nrows;
+              m &= m - 1;
+              if (prev_start >= 0 && ((k - 1) & 7) == gw) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int t = prev_start; t < start; ++t) {
+                  uint2 u = *reinterpret_cast<const uint2*>(base + t * 128 + ((ch ^ (t & 7)) << 4));
+                  acc.x += bf16_lo(u.x); acc.y += bf16_hi(u.x); acc.z += bf16_lo(u.y); acc.w += bf16_hi(u.y);
+                }
+                const bool open = (prev_start == 0 && head_open) || (start == nrows && tail_open);
+                float* dst = open ? a.agg_part + ((size_t)tile * 2 + (prev_start == 0 ? 0 : 1)) * 128
+                                  : a.agg + (size_t)sidx1[prev_start] * 128;
+                *reinterpret_cast<float4*>(dst + lane * 4) = acc;
+              }
+              prev_start = start;
+              ++k;
             }
-            bool complete = (b >= row0) && (e <= tile_end);
-            if (complete) a.agg[(size_t)n * 128 + c] = s;
-            else a.agg_part[((size_t)tile * 2 + (r == 0 ? 0 : 1)) * 128 + c] = s;
-            r = re;
           }
         }
       }
@@ -229,7 +258,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) umma_block_fwd_kernel(UmmaArgs a
   }
   fence_before_sync();
   __syncthreads();
-  if (tid < 32) tmem_dealloc<NWG * 128>(tmem_base);
+  if (tid < 32) tmem_dealloc<FWD_GROUPS * 128>(tmem_base);
 }
 
 // =============================================================================================
@@ -245,8 +274,8 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const __nv_bfloat
   uint64_t* mbar = reinterpret_cast<uint64_t*>(Bt + TILE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
   const int tid = threadIdx.x;
-  stage_rows<false>(At, Ag, nullptr, 0, 128, tid);
-  stage_rows<false>(Bt, Bg, nullptr, 0, 128, tid);
+  stage_rows<false, 128>(At, Ag, nullptr, 0, 128, tid);
+  stage_rows<false, 128>(Bt, Bg, nullptr, 0, 128, tid);
   if (tid == 0) {
     mbar_init(smem_u32(mbar), 1);
     fence_mbar_init();
@@ -275,8 +304,6 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const __nv_bfloat
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-constexpr int FWD_NWG = 2;
-
 size_t umma_prepared_bytes(int L) { return (size_t)(L + 2) * TILE_BYTES + (size_t)(L + 3) * 128 * sizeof(float); }
 
 int umma_prepare(const float* w, int L, void* prepared, cudaStream_t st) {
@@ -289,8 +316,9 @@ int umma_prepare(const float* w, int L, void* prepared, cudaStream_t st) {
   return AERO_OK;
 }
 
-static size_t fwd_smem(int L, int nwg) {
-  return 1024 + (size_t)(L + 2 + nwg) * TILE_BYTES + (size_t)(L + 3) * 512 + (size_t)nwg * 1024 + (size_t)nwg * 8 + 16;
+static size_t fwd_smem(int L) {
+  return 1024 + (size_t)(L + 2 + FWD_GROUPS) * TILE_BYTES + (size_t)(L + 3) * 512 +
+         (size_t)FWD_GROUPS * (1024 + 2048 + 32 + 8) + 16;
 }
 
 size_t umma_block_workspace_bytes(const aero_block_desc* d, int backward) {
@@ -313,15 +341,15 @@ int umma_block_fwd(const aero_block_desc* d, cudaStream_t st) {
   }
   if (d->rows == 0) return AERO_OK;
   static bool attr_set = false;
-  size_t smem = fwd_smem(d->L, FWD_NWG);
   if (!attr_set) {
-    AERO_CUDA(cudaFuncSetAttribute(umma_block_fwd_kernel<FWD_NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)fwd_smem(UMMA_MAX_L, FWD_NWG)));
+    AERO_CUDA(cudaFuncSetAttribute(umma_block_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)fwd_smem(UMMA_MAX_L)));
     attr_set = true;
   }
   int64_t tiles = cdiv(d->rows, 128);
-  int grid = (int)(cdiv(tiles, FWD_NWG) < sm_count() ? cdiv(tiles, FWD_NWG) : sm_count());
-  umma_block_fwd_kernel<FWD_NWG><<<grid, FWD_NWG * 128, smem, st>>>(a);
+  int64_t want = cdiv(tiles, FWD_GROUPS);
+  int grid = (int)(want < sm_count() ? want : sm_count());
+  umma_block_fwd_kernel<<<grid, FWD_THREADS, fwd_smem(d->L), st>>>(a);
   AERO_LAUNCH_CHECK();
   if (d->agg) return launch_agg_fixup(a.agg_part, d->rowptr, d->agg, d->rows, d->n_nodes, 128, d->idx1, st);
   return AERO_OK;

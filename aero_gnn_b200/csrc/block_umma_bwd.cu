@@ -1,8 +1,8 @@
 // block_umma_bwd.cu -- backward of the fused MGN block on tcgen05 tensor cores.
 //
-// One persistent CTA (128 threads) per SM owns one 128-row tile at a time and runs, per tile,
+// One persistent CTA (512 threads, 16 warps) per SM owns one 128-row tile at a time and runs, per tile,
 //   forward recompute : (L+2) GEMMs   h_m = act(h_{m-1} W_m^T + ..),  y = h_L W_out^T + b
-//   LayerNorm backward in registers (thread = row): dL/dy, plus the column sums for d(gamma), d(beta)
+//   LayerNorm backward (thread = (row, 32-column chunk), row statistics exchanged through shared memory): dL/dy
 //   for m = L+1 .. 1  : dW_m += G_m^T H_{m-1}   (both operands MN-major views of the same row tiles,
 //                                               fp32 accumulators stay in TMEM for the whole kernel)
 //                       G_{m-1} = (G_m W_m) * act'(H_{m-1})   (W_m read as an MN-major operand), written in place
@@ -13,28 +13,16 @@
 // Shared memory holds max(L+2,3) activation tiles and TWO weight slots; weight matrix m lives in slot (m & 1) and
 // is streamed from the L2-resident bf16 image with cp.async.bulk one GEMM ahead (4 x 32 KB per tile for L = 2).
 // TMEM: columns [0,128) working accumulator, [128 m, 128 m + 128) the dW_m accumulator (512 columns for L = 2).
-// Bias / LayerNorm-parameter gradients are column sums taken by thread = column over the bf16 tiles while the
-// MMAs run.  Per-CTA partial gradients are written once at the end and reduced in CTA order (deterministic).
+// Epilogues: warp w reads TMEM lanes 32*(w%4).., columns 32*(w/4)..; one 32-column chunk per thread.
+// Bias / LayerNorm-parameter gradients are column sums over the bf16 tiles (thread = (column, row quarter)),
+// taken while the MMAs run.  Per-CTA partial gradients are written once at the end and reduced in CTA order.
 #include "umma_block.cuh"
 
 namespace aero {
 
-constexpr int BWD_THREADS = 128;
+constexpr int BWD_THREADS = 512;
 
 __device__ __forceinline__ int h_tile(int m) { return m == 0 ? 1 : (m == 1 ? 0 : m); }   // tile holding H_m
-
-// column sum of a bf16 row tile: thread = column c, rows in order
-__device__ __forceinline__ float tile_col_sum(const uint8_t* tile, int c) {
-  const uint8_t* colp = tile + (c >> 6) * PANEL_BYTES + (c & 7) * 2;
-  const int cc = (c >> 3) & 7;
-  float s = 0.f;
-#pragma unroll 8
-  for (int t = 0; t < 128; ++t) {
-    uint16_t h = *reinterpret_cast<const uint16_t*>(colp + t * 128 + ((cc ^ (t & 7)) << 4));
-    s += __uint_as_float((uint32_t)h << 16);
-  }
-  return s;
-}
 
 __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -46,11 +34,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
   float* vec = reinterpret_cast<float*>(X + (size_t)NT * TILE_BYTES);
   int* sidx0 = reinterpret_cast<int*>(vec + (L + 3) * 128);
   int* sidx1 = sidx0 + 128;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(sidx1 + 128);   // [0] mma, [1..2] weight slots
+  float* red = reinterpret_cast<float*>(sidx1 + 128);          // [4 chunks][128 rows][2]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 1024);    // [0] mma, [1..2] weight slots
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 3);
 
-  const int tid = threadIdx.x, q = tid >> 5;
-  const int row = tid;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int q = wid & 3;         // TMEM lane quarter
+  const int ch = wid >> 2;       // 32-column chunk owned in epilogues
+  const int row = q * 32 + lane;
   {
     const float* vs = reinterpret_cast<const float*>(a.prep + (size_t)(L + 2) * TILE_BYTES);
     for (int i = tid; i < (L + 3) * 128; i += BWD_THREADS) vec[i] = vs[i];
@@ -74,11 +65,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
   const uint32_t g_s = x_s + (uint32_t)(NT - 1) * TILE_BYTES;
   const int act = a.act;
 
-  // ---- weight streaming state (thread 0 only) ----
+  // ---- weight streaming state (used by thread 0 only) ----
   int slot_mat[2] = {-1, -1};
   bool slot_pending[2] = {false, false};
   uint32_t slot_phase[2] = {0, 0};
-  auto prefetch = [&](int m) {   // thread 0
+  auto prefetch = [&](int m) {
     int s = m & 1;
     if (slot_mat[s] == m) return;
     uint32_t bar = smem_u32(&mbar[1 + s]);
@@ -87,7 +78,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
     slot_mat[s] = m;
     slot_pending[s] = true;
   };
-  auto acquire = [&](int m) -> uint32_t {   // thread 0: weight m resident -> its smem address
+  auto acquire = [&](int m) -> uint32_t {
     int s = m & 1;
     if (slot_mat[s] != m) prefetch(m);
     if (slot_pending[s]) {
@@ -99,7 +90,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
   };
   if (tid == 0) {
     prefetch(0);
-    if (L + 1 >= 1) prefetch(1);
+    prefetch(1);
   }
 
   uint32_t phase = 0;
@@ -116,18 +107,19 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
     const bool valid = row < nrows;
     __syncthreads();   // previous tile fully consumed
     // ---- stage main rows, gather indices, and the incoming gradient tile (g_out + g_agg[receiver]) ----
-    if (a.main_f32) stage_rows<true>(X, a.main, a.main_scale, row0, nrows, tid);
-    else stage_rows<false>(X, a.main, nullptr, row0, nrows, tid);
-    {
+    if (a.main_f32) stage_rows<true, BWD_THREADS>(X, a.main, a.main_scale, row0, nrows, tid);
+    else stage_rows<false, BWD_THREADS>(X, a.main, nullptr, row0, nrows, tid);
+    if (tid < 128) {
       int64_t r = row0 + tid;
-      sidx0[tid] = valid ? (a.idx0 ? a.idx0[r] : (int)r) : 0;
-      sidx1[tid] = valid ? (a.idx1 ? a.idx1[r] : -1) : -1;
+      bool ok = tid < nrows;
+      sidx0[tid] = ok ? (a.idx0 ? a.idx0[r] : (int)r) : 0;
+      sidx1[tid] = ok ? (a.idx1 ? a.idx1[r] : -1) : -1;
     }
     {
       const int chunk = tid & 15;
-#pragma unroll 4
-      for (int i = 0; i < 16; ++i) {
-        int r = (tid >> 4) + i * 8;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int r = (tid >> 4) + i * 32;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (r < nrows) {
           v = *reinterpret_cast<const uint4*>(a.g_out + (row0 + r) * 128 + chunk * 8);
@@ -147,6 +139,26 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
     }
     fence_async_smem();
     __syncthreads();
+    // pull the next tile's rows into L2 while this one computes (HBM latency off the critical path)
+    {
+      const int64_t nrow0 = (tile + gridDim.x) * 128;
+      if (nrow0 < a.rows) {
+        const int64_t r = nrow0 + (tid >> 2);
+        if (r < a.rows) {
+          const int part4 = tid & 3;
+          if (part4 < 2) {
+            if (a.main_f32) {
+              prefetch_l2(reinterpret_cast<const float*>(a.main) + r * 128 + part4 * 64);
+              prefetch_l2(reinterpret_cast<const float*>(a.main) + r * 128 + part4 * 64 + 32);
+            } else {
+              prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(a.main) + r * 128 + part4 * 64);
+            }
+          } else {
+            prefetch_l2(a.g_out + r * 128 + (part4 - 2) * 64);
+          }
+        }
+      }
+    }
 
     // ---- forward recompute ----
     for (int m = 0; m <= L + 1; ++m) {
@@ -158,7 +170,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
         mma_commit(bar_mma);
         if (m + 1 <= L + 1) prefetch(m + 1);   // other slot: last read by GEMM m-1, already complete
       }
-      if (m == 0) dbet += tile_col_sum(G, tid);   // d(beta) column sum of the incoming gradient, under the MMA
+      if (m == 0) dbet += tile_col_sums_512(G, wid, lane);   // d(beta): column sum of the incoming gradient, under the MMA
       mbar_wait(bar_mma, phase);
       phase ^= 1;
       fence_after_sync();
@@ -170,106 +182,90 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
           p0 = a.P + (int64_t)sidx0[row] * a.ldp + a.poff0;
           if (sidx1[row] >= 0) p1 = a.P + (int64_t)sidx1[row] * a.ldp + a.poff1;
         }
-        const float* bias = m > 0 ? vec + (m - 1) * 128 : nullptr;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint4 g0[4], g1[4];
-          if (m == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              g0[j] = p0 ? *reinterpret_cast<const uint4*>(p0 + c * 32 + j * 8) : make_uint4(0u, 0u, 0u, 0u);
-              g1[j] = p1 ? *reinterpret_cast<const uint4*>(p1 + c * 32 + j * 8) : make_uint4(0u, 0u, 0u, 0u);
-            }
-          }
-          float v[32];
-          tmem_ld32(tlane + (uint32_t)(c * 32), v);
-          if (m == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              add_bf16x8(v + 8 * j, g0[j]);
-              add_bf16x8(v + 8 * j, g1[j]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += bias[c * 32 + j];
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = valid ? relu_or_act(v[j], act) : 0.f;
-          store_row32(Ht, row, c, v);
-        }
+        hidden_epilogue_chunk(tlane, ch, p0, p1, m > 0 ? vec + (m - 1) * 128 : nullptr, act, Ht, row);
         fence_before_sync();
         fence_async_smem();
         __syncthreads();
       }
     }
-    // ---- LayerNorm backward (thread = row); G holds g = dL/d(out) and ends up holding dL/dy ----
+    // ---- LayerNorm backward; G holds g = dL/d(out) and ends up holding dL/dy ----
     {
-      float v[128];
-      const float* bo = vec + L * 128;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float t[32];
-        tmem_ld32(tlane + (uint32_t)(c * 32), t);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[c * 32 + j] = t[j] + bo[c * 32 + j];
-      }
+      float v[32];
+      tmem_ld32(tlane + (uint32_t)(ch * 32), v);
       fence_before_sync();
+      const float* bo = vec + L * 128 + ch * 32;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 b4 = *reinterpret_cast<const float4*>(bo + 4 * j);
+        v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+      }
       if (a.use_ln) {
-        float s = 0.f;
+        float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 128; ++j) s += v[j];
-        const float mean = s * (1.f / 128.f);
-        float ss = 0.f;
-#pragma unroll
-        for (int j = 0; j < 128; ++j) {
-          float d = v[j] - mean;
-          ss = fmaf(d, d, ss);
+        for (int j = 0; j < 32; j += 2) {
+          s0 += v[j]; s1 += v[j + 1];
+          t0 = fmaf(v[j], v[j], t0); t1 = fmaf(v[j + 1], v[j + 1], t1);
         }
-        const float rstd = rsqrtf(ss * (1.f / 128.f) + 1e-5f);
-        const float* gam = vec + (L + 1) * 128;
-        float m1 = 0.f, m2 = 0.f;
-        uint32_t gp[64];
+        red[(ch * 128 + row) * 2] = s0 + s1;
+        red[(ch * 128 + row) * 2 + 1] = t0 + t1;
+        __syncthreads();
+        float s = 0.f, t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          s += red[(k * 128 + row) * 2];
+          t += red[(k * 128 + row) * 2 + 1];
+        }
+        const float mean = s * (1.f / 128.f);
+        const float rstd = rsqrtf(fmaxf(t * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
+        const float* gam = vec + (L + 1) * 128 + ch * 32;
+        // this thread's 32 gradient values (4 x 16 B of the G tile)
+        uint32_t gp[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 g4 = *reinterpret_cast<const uint4*>(G + tile_chunk_off(row, ch * 4 + j));
+          gp[4 * j] = g4.x; gp[4 * j + 1] = g4.y; gp[4 * j + 2] = g4.z; gp[4 * j + 3] = g4.w;
+        }
+        float m1a = 0.f, m1b = 0.f, m2a = 0.f, m2b = 0.f;
+        uint32_t zp[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          uint4 g4 = *reinterpret_cast<const uint4*>(G + tile_chunk_off(row, j));
-          gp[4 * j + 0] = g4.x; gp[4 * j + 1] = g4.y; gp[4 * j + 2] = g4.z; gp[4 * j + 3] = g4.w;
-          float z[8];
+          float glo = bf16_lo(gp[j]), ghi = bf16_hi(gp[j]);
+          float hlo = (v[2 * j] - mean) * rstd, hhi = (v[2 * j + 1] - mean) * rstd;
+          v[2 * j] = hlo;
+          v[2 * j + 1] = hhi;
+          float wlo = glo * gam[2 * j], whi = ghi * gam[2 * j + 1];
+          m1a += wlo; m1b += whi;
+          m2a = fmaf(wlo, hlo, m2a); m2b = fmaf(whi, hhi, m2b);
+          zp[j] = pack_bf16(glo * hlo, ghi * hhi);
+        }
+        __syncthreads();   // everyone has read the row statistics -> red can be reused
+        red[(ch * 128 + row) * 2] = m1a + m1b;
+        red[(ch * 128 + row) * 2 + 1] = m2a + m2b;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float glo = bf16_lo(gp[4 * j + k]), ghi = bf16_hi(gp[4 * j + k]);
-            float hlo = (v[8 * j + 2 * k] - mean) * rstd, hhi = (v[8 * j + 2 * k + 1] - mean) * rstd;
-            v[8 * j + 2 * k] = hlo;
-            v[8 * j + 2 * k + 1] = hhi;
-            float wlo = glo * gam[8 * j + 2 * k], whi = ghi * gam[8 * j + 2 * k + 1];
-            m1 += wlo + whi;
-            m2 = fmaf(wlo, hlo, fmaf(whi, hhi, m2));
-            z[2 * k] = glo * hlo;
-            z[2 * k + 1] = ghi * hhi;
-          }
-          uint4 zq;
-          zq.x = pack_bf16(z[0], z[1]); zq.y = pack_bf16(z[2], z[3]);
-          zq.z = pack_bf16(z[4], z[5]); zq.w = pack_bf16(z[6], z[7]);
-          *reinterpret_cast<uint4*>(G + tile_chunk_off(row, j)) = zq;   // z = g * yhat, for d(gamma)
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(G + tile_chunk_off(row, ch * 4 + j)) = make_uint4(zp[4 * j], zp[4 * j + 1], zp[4 * j + 2], zp[4 * j + 3]);
+        __syncthreads();
+        dgam += tile_col_sums_512(G, wid, lane);   // d(gamma) column sum of z = g * yhat
+        float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          m1 += red[(k * 128 + row) * 2];
+          m2 += red[(k * 128 + row) * 2 + 1];
         }
         m1 *= (1.f / 128.f);
         m2 *= (1.f / 128.f);
-        __syncthreads();
-        dgam += tile_col_sum(G, tid);
-        __syncthreads();
+        __syncthreads();   // z fully consumed
+        uint32_t op[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float o[8];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float glo = bf16_lo(gp[4 * j + k]), ghi = bf16_hi(gp[4 * j + k]);
-            o[2 * k] = rstd * (glo * gam[8 * j + 2 * k] - m1 - v[8 * j + 2 * k] * m2);
-            o[2 * k + 1] = rstd * (ghi * gam[8 * j + 2 * k + 1] - m1 - v[8 * j + 2 * k + 1] * m2);
-          }
-          uint4 oq;
-          oq.x = pack_bf16(o[0], o[1]); oq.y = pack_bf16(o[2], o[3]);
-          oq.z = pack_bf16(o[4], o[5]); oq.w = pack_bf16(o[6], o[7]);
-          *reinterpret_cast<uint4*>(G + tile_chunk_off(row, j)) = oq;
+          float glo = bf16_lo(gp[j]), ghi = bf16_hi(gp[j]);
+          float olo = rstd * (glo * gam[2 * j] - m1 - v[2 * j] * m2);
+          float ohi = rstd * (ghi * gam[2 * j + 1] - m1 - v[2 * j + 1] * m2);
+          op[j] = pack_bf16(olo, ohi);
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(G + tile_chunk_off(row, ch * 4 + j)) = make_uint4(op[4 * j], op[4 * j + 1], op[4 * j + 2], op[4 * j + 3]);
       }
       // use_ln == 0: dL/dy = g, already in G
       fence_async_smem();
@@ -290,45 +286,17 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
         mma_commit(bar_mma);
         if (m >= 1) prefetch(m - 1);
       }
-      if (m >= 1) db[m - 1] += tile_col_sum(Gc, tid);   // bias gradient of Linear m (index m-1: 0..L-1 hidden, L out)
-      if (m == 0) {
-        // g_h0 leaves through a coalesced copy of its tile while the last GEMM runs
-        const int chunk = tid & 15;
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-          int r = (tid >> 4) + i * 8;
-          if (r < nrows)
-            *reinterpret_cast<uint4*>(a.g_h0 + (row0 + r) * 128 + chunk * 8) =
-                *reinterpret_cast<const uint4*>(Gc + tile_chunk_off(r, chunk));
-        }
-      }
+      if (m >= 1) db[m - 1] += tile_col_sums_512(Gc, wid, lane);   // bias gradient of Linear m
+      if (m == 0) unstage_rows<BWD_THREADS>(Gc, a.g_h0, row0, nrows, tid);   // g_h0 leaves while the last GEMM runs
       mbar_wait(bar_mma, phase);
       phase ^= 1;
       fence_after_sync();
       if (m >= 1) {
         uint8_t* Ht = X + (size_t)h_tile(m - 1) * TILE_BYTES;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          float v[32];
-          tmem_ld32(tlane + (uint32_t)(c * 32), v);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 h4 = *reinterpret_cast<const uint4*>(Ht + tile_chunk_off(row, c * 4 + j));
-            uint32_t hh[4] = {h4.x, h4.y, h4.z, h4.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float hlo = bf16_lo(hh[k]), hhi = bf16_hi(hh[k]);
-              if (act == AERO_ACT_RELU) {
-                v[8 * j + 2 * k] = hlo > 0.f ? v[8 * j + 2 * k] : 0.f;
-                v[8 * j + 2 * k + 1] = hhi > 0.f ? v[8 * j + 2 * k + 1] : 0.f;
-              } else {
-                v[8 * j + 2 * k] *= act_grad_from_out(hlo, act);
-                v[8 * j + 2 * k + 1] *= act_grad_from_out(hhi, act);
-              }
-            }
-          }
-          store_row32(Ht, row, c, v);   // in place: G_{m-1} over H_{m-1}
-        }
+        float v[32];
+        tmem_ld32(tlane + (uint32_t)(ch * 32), v);
+        mask_by_act_grad(v, Ht, row, ch, act);
+        store_row32(Ht, row, ch, v);   // in place: G_{m-1} over H_{m-1}
         fence_before_sync();
         fence_async_smem();
         __syncthreads();
@@ -336,69 +304,70 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
         gc_s = x_s + (uint32_t)h_tile(m - 1) * TILE_BYTES;
       } else {
         // g_main = G_0 W_main (* scale) (+ residual gradient)
-        const float sc = (a.main_scale && valid) ? a.main_scale[row0 + row] : 1.f;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          float v[32];
-          tmem_ld32(tlane + (uint32_t)(c * 32), v);
-          if (valid) {
+        float v[32];
+        tmem_ld32(tlane + (uint32_t)(ch * 32), v);
+        fence_before_sync();
+        if (valid) {
+          if (a.main_scale) {
+            const float sc = a.main_scale[row0 + row];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= sc;
-            if (a.has_resid_grad) {
-              const uint4* gr = reinterpret_cast<const uint4*>(a.g_out + (row0 + row) * 128 + c * 32);
-              const float* ga = a.g_agg ? a.g_agg + (size_t)sidx1[row] * 128 + c * 32 : nullptr;
+          }
+          if (a.has_resid_grad) {
+            const uint4* gr = reinterpret_cast<const uint4*>(a.g_out + (row0 + row) * 128 + ch * 32);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                add_bf16x8(v + 8 * j, gr[j]);
-                if (ga) {
+            for (int j = 0; j < 4; ++j) add_bf16x8(v + 8 * j, gr[j]);
+            if (a.g_agg) {
+              const float4* ga = reinterpret_cast<const float4*>(a.g_agg + (size_t)sidx1[row] * 128 + ch * 32);
 #pragma unroll
-                  for (int k = 0; k < 8; ++k) v[8 * j + k] += ga[8 * j + k];
-                }
-              }
-            }
-            if (a.main_f32) {
-              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.g_main) + (row0 + row) * 128 + c * 32);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            } else {
-              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.g_main) + (row0 + row) * 128 + c * 32);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 o4;
-                o4.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]); o4.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-                o4.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o4.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-                op[j] = o4;
+              for (int j = 0; j < 8; ++j) {
+                float4 t4 = ga[j];
+                v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
               }
             }
           }
+          if (a.main_f32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.g_main) + (row0 + row) * 128 + ch * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.g_main) + (row0 + row) * 128 + ch * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o4;
+              o4.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]); o4.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+              o4.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o4.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+              op[j] = o4;
+            }
+          }
         }
-        fence_before_sync();
       }
     }
     first_tile = false;
   }
 
-  // ---- flush per-CTA partial gradients: dW_m from TMEM, vectors from registers ----
+  // ---- flush per-CTA partial gradients: dW_m from TMEM, vectors from registers (row quarters summed in order) ----
   __syncthreads();
   fence_after_sync();
   const PackedLayout pl{L};
-  float* part = a.w_part + (size_t)blockIdx.x * pl.total();
+  float* part_out = a.w_part + (size_t)blockIdx.x * pl.total();
   for (int m = 1; m <= L + 1; ++m) {
-    float* dst = part + (m == L + 1 ? pl.w_out() : pl.w_hidden(m - 1)) + (size_t)row * 128;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      float v[32];
-      tmem_ld32(tlane + (uint32_t)(128 * m + c * 32), v);
+    float* dst = part_out + (m == L + 1 ? pl.w_out() : pl.w_hidden(m - 1)) + (size_t)row * 128 + ch * 32;
+    float v[32];
+    tmem_ld32(tlane + (uint32_t)(128 * m + ch * 32), v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(dst + c * 32 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    }
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   }
-  for (int l = 0; l < L; ++l) part[pl.b_hidden(l) + tid] = db[l];
-  part[pl.b_out() + tid] = db[L];
-  part[pl.gamma() + tid] = dgam;
-  part[pl.beta() + tid] = dbet;
   fence_before_sync();
+  // vectors: lanes with (lane & 3) == 0 own one column each (tile_col_sums_512)
+  if ((lane & 3) == 0) {
+    const int c = col_of_lane_512(wid, lane);
+    for (int l = 0; l < L; ++l) part_out[pl.b_hidden(l) + c] = db[l];
+    part_out[pl.b_out() + c] = db[L];
+    part_out[pl.gamma() + c] = dgam;
+    part_out[pl.beta() + c] = dbet;
+  }
   __syncthreads();
   if (tid < 32) tmem_dealloc<512>(tmem_base);
 }
@@ -406,7 +375,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
 // ---- host side ------------------------------------------------------------------------------------
 static size_t bwd_smem(int L) {
   int nt = (L + 2) > 3 ? (L + 2) : 3;
-  return 1024 + (size_t)(2 + nt) * TILE_BYTES + (size_t)(L + 3) * 512 + 1024 + 3 * 8 + 16;
+  return 1024 + (size_t)(2 + nt) * TILE_BYTES + (size_t)(L + 3) * 512 + 1024 + 4096 + 3 * 8 + 16;
 }
 static int bwd_grid_umma(int64_t rows) {
   int64_t tiles = cdiv(rows > 0 ? rows : 1, 128);

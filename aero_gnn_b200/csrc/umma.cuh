@@ -114,14 +114,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t saddr, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// bounded wait: a protocol bug traps (fails the launch) instead of hanging the GPU
+// bounded wait with back-off: a protocol bug traps (fails the launch) instead of hanging the GPU, and waiting
+// warps do not steal issue slots from the warps doing epilogue work
 __device__ __forceinline__ void mbar_wait(uint32_t saddr, uint32_t parity) {
   if (mbar_try_wait(saddr, parity)) return;
-  long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(saddr, parity)) {
-    if (clock64() - t0 > 4000000000LL) asm volatile("trap;\n");
+    __nanosleep(40);
+    if (++spins > (1u << 24)) asm volatile("trap;\n");
   }
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t saddr, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(saddr), "r"(bytes) : "memory");
 }

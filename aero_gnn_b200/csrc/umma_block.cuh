@@ -27,20 +27,30 @@ struct UmmaArgs {
   float* w_part;
 };
 
+constexpr int UMMA_MAX_L = 2;
+constexpr int UMMA_MAX_L_BWD = 2;
+size_t umma_bwd_workspace_bytes(const aero_block_desc* d);
+
 // ---- helpers --------------------------------------------------------------------------------------
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
   uint32_t s = smem_u32(p);
   return p + (((s + 1023u) & ~1023u) - s);
 }
 
-// stage rows [row0, row0+nrows) of a [rows,128] matrix into a row tile (zero padded), by one warpgroup
-template <bool F32>
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// stage rows [row0, row0+nrows) of a [rows,128] matrix into a row tile (zero padded) with NT cooperating
+// threads (t = 0..NT-1): a warp covers two whole rows per pass, so global reads are fully coalesced
+template <bool F32, int NT>
 __device__ __forceinline__ void stage_rows(uint8_t* tile, const void* src, const float* scale, int64_t row0, int nrows,
-                                           int wt) {
-  const int chunk = wt & 15;
+                                           int t) {
+  const int chunk = t & 15;
+  constexpr int RPP = NT / 16;   // rows per pass
 #pragma unroll 4
-  for (int i = 0; i < 16; ++i) {
-    int r = (wt >> 4) + i * 8;
+  for (int i = 0; i < 128 / RPP; ++i) {
+    int r = (t >> 4) + i * RPP;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (r < nrows) {
       if (F32) {
@@ -57,6 +67,19 @@ __device__ __forceinline__ void stage_rows(uint8_t* tile, const void* src, const
       }
     }
     *reinterpret_cast<uint4*>(tile + tile_chunk_off(r, chunk)) = v;
+  }
+}
+
+// copy the valid rows of a row tile to a [rows,128] bf16 matrix (coalesced), NT cooperating threads
+template <int NT>
+__device__ __forceinline__ void unstage_rows(const uint8_t* tile, __nv_bfloat16* dst, int64_t row0, int nrows, int t) {
+  const int chunk = t & 15;
+  constexpr int RPP = NT / 16;
+#pragma unroll 4
+  for (int i = 0; i < 128 / RPP; ++i) {
+    int r = (t >> 4) + i * RPP;
+    if (r < nrows)
+      *reinterpret_cast<uint4*>(dst + (row0 + r) * 128 + chunk * 8) = *reinterpret_cast<const uint4*>(tile + tile_chunk_off(r, chunk));
   }
 }
 
@@ -92,9 +115,109 @@ __device__ __forceinline__ void store_row32(uint8_t* tile, int row, int c32, con
 
 __device__ __forceinline__ float relu_or_act(float v, int act) { return act == AERO_ACT_RELU ? fmaxf(v, 0.f) : act_fwd(v, act); }
 
-constexpr int UMMA_MAX_L = 2;
-constexpr int UMMA_MAX_L_BWD = 2;
-size_t umma_bwd_workspace_bytes(const aero_block_desc* d);
+// hidden-layer epilogue for one (row, 32-column chunk): accumulator + (gathered pre-projections | bias),
+// activation, bf16, into the destination row tile.  p0/p1: gathered rows (layer 0) or nullptr; bias: smem.
+__device__ __forceinline__ void hidden_epilogue_chunk(uint32_t tacc_lane, int c, const __nv_bfloat16* p0,
+                                                      const __nv_bfloat16* p1, const float* bias, int act,
+                                                      uint8_t* dst_tile, int row) {
+  uint4 g0[4], g1[4];
+  if (p0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g0[j] = *reinterpret_cast<const uint4*>(p0 + c * 32 + j * 8);
+  }
+  if (p1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g1[j] = *reinterpret_cast<const uint4*>(p1 + c * 32 + j * 8);
+  }
+  float v[32];
+  tmem_ld32(tacc_lane + (uint32_t)(c * 32), v);
+  if (p0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) add_bf16x8(v + 8 * j, g0[j]);
+  }
+  if (p1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) add_bf16x8(v + 8 * j, g1[j]);
+  }
+  if (bias) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 b4 = *reinterpret_cast<const float4*>(bias + c * 32 + 4 * j);
+      v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+    }
+  }
+  if (act == AERO_ACT_RELU) {   // uniform branch: the transcendental activations stay out of the hot path
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], act);
+  }
+  store_row32(dst_tile, row, c, v);
+}
+
+// v[j] *= act'(h[j]) for the 32 activations h stored at (row, chunk c) of a bf16 row tile
+__device__ __forceinline__ void mask_by_act_grad(float* v, const uint8_t* h_tile_ptr, int row, int c, int act) {
+  uint32_t hh[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 h4 = *reinterpret_cast<const uint4*>(h_tile_ptr + tile_chunk_off(row, c * 4 + j));
+    hh[4 * j] = h4.x; hh[4 * j + 1] = h4.y; hh[4 * j + 2] = h4.z; hh[4 * j + 3] = h4.w;
+  }
+  if (act == AERO_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      // bf16 sign/zero tests on the packed halves: h > 0  <=>  (bits & 0x7fff) != 0 and sign clear
+      v[2 * j] = (int)(hh[j] << 16) > 0 ? v[2 * j] : 0.f;
+      v[2 * j + 1] = (int)(hh[j] & 0xffff0000u) > 0 ? v[2 * j + 1] : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      v[2 * j] *= act_grad_from_out(bf16_lo(hh[j]), act);
+      v[2 * j + 1] *= act_grad_from_out(bf16_hi(hh[j]), act);
+    }
+  }
+}
+
+// Column sums of a bf16 row tile by a 512-thread CTA: warp w owns the 8 columns of chunk w, lane l sums rows
+// l, l+32, l+64, l+96, then a recursive-halving shuffle reduction leaves the total of column 8*w + (l>>2 & 7)...
+// precisely: after the reduction lane l holds the total of column 8*w + colsel(l) where colsel(l) = ((l>>4)&1)*4 +
+// ((l>>3)&1)*2 + ((l>>2)&1); lanes with (l & 3) == 0 are the designated owners.  Fixed order -> deterministic.
+__device__ __forceinline__ float tile_col_sums_512(const uint8_t* tile, int warp, int lane) {
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int r = lane + 32 * i;
+    uint4 q = *reinterpret_cast<const uint4*>(tile + tile_chunk_off(r, warp));
+    s[0] += bf16_lo(q.x); s[1] += bf16_hi(q.x); s[2] += bf16_lo(q.y); s[3] += bf16_hi(q.y);
+    s[4] += bf16_lo(q.z); s[5] += bf16_hi(q.z); s[6] += bf16_lo(q.w); s[7] += bf16_hi(q.w);
+  }
+  // halve the vector, double the lane span: xor 16 keeps 4 values, xor 8 keeps 2, xor 4 keeps 1
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float t[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float mine = b4 ? s[4 + j] : s[j], give = b4 ? s[j] : s[4 + j];
+    t[j] = mine + __shfl_xor_sync(0xffffffffu, give, 16);
+  }
+  float u[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    float mine = b3 ? t[2 + j] : t[j], give = b3 ? t[j] : t[2 + j];
+    u[j] = mine + __shfl_xor_sync(0xffffffffu, give, 8);
+  }
+  float mine = b2 ? u[1] : u[0], give = b2 ? u[0] : u[1];
+  float w = mine + __shfl_xor_sync(0xffffffffu, give, 4);
+  w += __shfl_xor_sync(0xffffffffu, w, 2);
+  w += __shfl_xor_sync(0xffffffffu, w, 1);
+  return w;
+}
+__device__ __forceinline__ int col_of_lane_512(int warp, int lane) {
+  return 8 * warp + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+}
 
 static inline UmmaArgs make_uargs(const aero_block_desc* d) {
   UmmaArgs a;

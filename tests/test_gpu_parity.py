@@ -339,7 +339,12 @@ def test_bf16_layer_vs_fp32_oracle_and_grads():
     assert rel_l2(xo.float(), xr) < 1e-2 and rel_l2(eo.float(), er) < 1e-2
     gx_ref, ge_ref = torch.autograd.grad((torch.cat([xr, er], 0) * g["probe"]).sum(), [xr_in, er_in])
     (torch.cat([xo, eo], 0).float() * g["probe"].to(DEV)).sum().backward()
+    # yardstick: the reference's own bf16 mode (pure bf16 autograd, train.py:30-33) against the same fp32 truth
+    sd16 = {k: v.to(torch.bfloat16) for k, v in g["state"].items()}
+    x16r, e16r = x16.clone().requires_grad_(True), e16.clone().requires_grad_(True)
+    xq, eq = O.mgn_layer(sd16, "", x16r, e16r, ei, "add")
+    gx16, ge16 = torch.autograd.grad((torch.cat([xq, eq], 0).float() * g["probe"]).sum(), [x16r, e16r])
     ex, ee = rel_l2(xb.grad.float(), gx_ref), rel_l2(eb.grad.float(), ge_ref)
-    print("bf16 layer grad rel-L2 err:", ex, ee, " max-norm:", rel_err(xb.grad.float(), gx_ref),
-          rel_err(eb.grad.float(), ge_ref))
-    assert ex < 2e-2 and ee < 2e-2
+    bx, be = rel_l2(gx16.float(), gx_ref), rel_l2(ge16.float(), ge_ref)
+    print("bf16 layer grad rel-L2 err:", ex, ee, " reference bf16 mode:", bx, be)
+    assert ex <= max(1e-2, 1.5 * bx) and ee <= max(1e-2, 1.5 * be)
