@@ -1,0 +1,229 @@
+"""One large mesh across the GPUs of a box: contiguous receiver-node blocks + one halo exchange per step.
+
+The reference has no distributed code; this is new.  Rank r owns nodes [lo, hi) and every edge
+whose receiver it owns, so edge latents, the edge block and the receiver sums stay local and deterministic.  A
+processor step reads only 1-hop sender latents (mgnLayer.py:40-41), so the only data crossing ranks is the latent
+row of each remote sender ("halo"), once per step forward and the gradient of those rows once per step backward.
+Weights are replicated; their gradients are summed with one all-reduce after the backward pass.
+
+Local numbering: own nodes first (global id - lo), then halo nodes in ascending global id.  Because owners hold
+contiguous id ranges, the halo rows coming from one peer are a contiguous slice of the halo block.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .processor import D, StackConfig
+
+
+def block_bounds(n_nodes: int, world: int, rank: int):
+    blk = -(-n_nodes // world)
+    lo = min(rank * blk, n_nodes)
+    return lo, min(lo + blk, n_nodes)
+
+
+@dataclass
+class HaloPlan:
+    """Pure index plan (numpy / CPU): which rows to send to / receive from each peer."""
+
+    rank: int
+    world: int
+    lo: int
+    hi: int
+    edge_ids: np.ndarray            # global caller edge ids owned by this rank (ascending)
+    local_edge_index: np.ndarray    # [2, E_loc] int64: local sender id, local receiver id
+    halo_global: np.ndarray         # [n_halo] ascending global ids of remote senders
+    recv_counts: List[int]          # rows received from each peer (contiguous slices of the halo block)
+    send_idx: List[np.ndarray]      # own-local ids of the rows each peer needs, ascending global id
+
+    @property
+    def n_own(self) -> int:
+        return self.hi - self.lo
+
+    @property
+    def n_halo(self) -> int:
+        return int(self.halo_global.shape[0])
+
+    @property
+    def n_local(self) -> int:
+        return self.n_own + self.n_halo
+
+
+def build_halo_plan(edge_index: np.ndarray, n_nodes: int, rank: int, world: int) -> HaloPlan:
+    """Every rank holds the full connectivity (16E bytes), so the plan needs no communication."""
+    src, dst = edge_index[0], edge_index[1]
+    lo, hi = block_bounds(n_nodes, world, rank)
+    mine = np.flatnonzero((dst >= lo) & (dst < hi))
+    s, d = src[mine], dst[mine] - lo
+    remote = (s < lo) | (s >= hi)
+    halo = np.unique(s[remote])
+    loc = np.where(remote, (hi - lo) + np.searchsorted(halo, s), s - lo)
+    recv_counts, send_idx = [], []
+    for p in range(world):
+        plo, phi = block_bounds(n_nodes, world, p)
+        recv_counts.append(int(np.count_nonzero((halo >= plo) & (halo < phi))) if p != rank else 0)
+        if p == rank:
+            send_idx.append(np.empty(0, dtype=np.int64))
+            continue
+        theirs = (dst >= plo) & (dst < phi) & (src >= lo) & (src < hi)      # p's edges whose sender I own
+        send_idx.append(np.unique(src[theirs]) - lo)
+    return HaloPlan(rank, world, lo, hi, mine, np.stack([loc, d]).astype(np.int64), halo, recv_counts, send_idx)
+
+
+class HaloExchanger:
+    """Point-to-point halo exchange over torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, plan: HaloPlan, device, group=None):
+        self.plan, self.group = plan, group
+        self.send_idx = [torch.from_numpy(ix).to(device) for ix in plan.send_idx]
+        self.recv_off = np.concatenate([[0], np.cumsum(plan.recv_counts)]).astype(int)
+
+    def _p2p(self, sends: Sequence[Optional[torch.Tensor]], recvs: Sequence[Optional[torch.Tensor]]) -> None:
+        p2p = []
+        for p in range(self.plan.world):
+            if recvs[p] is not None and recvs[p].numel():
+                p2p.append(dist.P2POp(dist.irecv, recvs[p], p, self.group))
+        for p in range(self.plan.world):
+            if sends[p] is not None and sends[p].numel():
+                p2p.append(dist.P2POp(dist.isend, sends[p], p, self.group))
+        if p2p:
+            for req in dist.batch_isend_irecv(p2p):
+                req.wait()
+
+    def forward(self, x_own: torch.Tensor) -> torch.Tensor:
+        """Rows of the remote senders, [n_halo, width], in halo order."""
+        pl = self.plan
+        halo = x_own.new_empty((pl.n_halo, x_own.size(1)))
+        sends = [x_own[ix].contiguous() if ix.numel() else None for ix in self.send_idx]
+        recvs = [halo[self.recv_off[p]: self.recv_off[p + 1]] if pl.recv_counts[p] else None for p in range(pl.world)]
+        self._p2p(sends, recvs)
+        return halo
+
+    def backward(self, g_halo: torch.Tensor, g_own: torch.Tensor) -> None:
+        """Send halo-row gradients back to their owners; owners add them in ascending peer order (deterministic:
+        the rows one peer returns are distinct)."""
+        pl = self.plan
+        sends = [g_halo[self.recv_off[p]: self.recv_off[p + 1]].contiguous() if pl.recv_counts[p] else None
+                 for p in range(pl.world)]
+        recvs = [g_own.new_empty((ix.numel(), g_own.size(1))) if ix.numel() else None for ix in self.send_idx]
+        self._p2p(sends, recvs)
+        for p in range(pl.world):
+            if recvs[p] is not None:
+                g_own.index_add_(0, self.send_idx[p], recvs[p])
+
+
+class PartitionedStackFn(torch.autograd.Function):
+    """MGN processor stack on one receiver block; apply(cfg, part, x_own, e_csr, *flat) like processor.MGNStackFn."""
+
+    @staticmethod
+    def forward(ctx, cfg: StackConfig, part: "PartitionedProcessor", x, e, *flat):
+        plan, ex = part.plan, part.exchanger
+        n_own = part.n_own
+        K = len(flat) // 4
+        x, e = x.contiguous(), e.contiguous()
+        path_e = ops.choose_path(x.dtype, cfg.act_edge, cfg.L_edge)
+        path_n = ops.choose_path(x.dtype, cfg.act_node, cfg.L_node)
+        scale = plan.inv_deg[:n_own].contiguous() if cfg.mean else None
+        saved = []
+        for k in range(K):
+            w_edge, w_node, w_proj, b_proj = flat[4 * k: 4 * k + 4]
+            pe = ops.PreparedBlock(w_edge.detach(), cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
+            pn = ops.PreparedBlock(w_node.detach(), cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
+            x_ext = torch.cat([x, ex.forward(x)], dim=0)
+            P = torch.addmm(b_proj.detach(), x_ext, w_proj.detach().t())
+            e_new, agg = ops.block_fwd(pe, e, e, P, plan.src, plan.dst, 0, D, rowptr=plan.rowptr, want_agg=True,
+                                       kind="edge_fwd")
+            agg = agg[:n_own]
+            x_new, _ = ops.block_fwd(pn, agg, x, P, None, None, 2 * D, 0, main_scale=scale, kind="node_fwd")
+            saved += [x, e, agg]
+            x, e = x_new, e_new
+        ctx.cfg, ctx.part, ctx.K = cfg, part, K
+        ctx.paths = (ops.choose_path(x.dtype, cfg.act_edge, cfg.L_edge, backward=True),
+                     ops.choose_path(x.dtype, cfg.act_node, cfg.L_node, backward=True))
+        ctx.save_for_backward(*saved, *flat)
+        return x, e
+
+    @staticmethod
+    def backward(ctx, G_x, G_e):
+        cfg, part, K = ctx.cfg, ctx.part, ctx.K
+        plan, ex, n_own = part.plan, part.exchanger, part.n_own
+        path_e, path_n = ctx.paths
+        saved = ctx.saved_tensors
+        acts, flat = saved[: 3 * K], saved[3 * K:]
+        dt = acts[0].dtype
+        G_x = G_x.contiguous().to(dt)
+        G_e = G_e.contiguous().to(dt).clone()
+        scale = plan.inv_deg[:n_own].contiguous() if cfg.mean else None
+        grads = [None] * (4 * K)
+        for k in reversed(range(K)):
+            x, e, agg = acts[3 * k: 3 * k + 3]
+            w_edge, w_node, w_proj, b_proj = flat[4 * k: 4 * k + 4]
+            pe = ops.PreparedBlock(w_edge, cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
+            pn = ops.PreparedBlock(w_node, cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
+            x_ext = torch.cat([x, ex.forward(x)], dim=0)
+            P = torch.addmm(b_proj, x_ext, w_proj.t())
+            g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale, kind="node_bwd")
+            agg_eff = agg if scale is None else agg * scale[:, None]
+            g_wn[: D * D] = (g_h0n.t() @ agg_eff.to(dt)).float().reshape(-1)
+            G_e, g_h0e, g_we = ops.block_bwd(pe, e, P, plan.src, plan.dst, 0, D, G_e, g_agg=g_agg, has_resid_grad=True,
+                                             g_main_out=G_e, kind="edge_bwd")
+            g_we[: D * D] = (g_h0e.t() @ e).float().reshape(-1)
+            g_ps = ops.segment_reduce(g_h0e, plan.sptr, plan.sperm, plan.N)
+            g_pd = ops.segment_reduce(g_h0e, plan.rowptr, None, plan.N)
+            w_s, w_d, w_nx = w_proj[:D], w_proj[D:2 * D], w_proj[2 * D:]
+            g_ext = torch.addmm(g_ps @ w_s, g_pd, w_d)              # [n_local, D]
+            g_x = G_x + g_ext[:n_own]
+            g_x.addmm_(g_h0n, w_nx)
+            ex.backward(g_ext[n_own:], g_x)
+            g_wproj = torch.cat([g_ps.t() @ x_ext, g_pd.t() @ x_ext, g_h0n.t() @ x], dim=0)
+            g_bproj = torch.cat([g_ps.float().sum(0), g_pd.float().sum(0), g_h0n.float().sum(0)]).to(dt)
+            grads[4 * k: 4 * k + 4] = [g_we, g_wn, g_wproj.to(w_proj.dtype), g_bproj.to(b_proj.dtype)]
+            G_x = g_x
+        return (None, None, G_x, G_e, *grads)
+
+
+class PartitionedProcessor:
+    """Receiver-block partition of one mesh for this rank: halo plan, local graph plan, exchange, grad all-reduce."""
+
+    def __init__(self, edge_index: torch.Tensor, n_nodes: int, rank: int, world: int, device, group=None):
+        ei = edge_index.cpu().numpy()
+        self.halo = build_halo_plan(ei, n_nodes, rank, world)
+        self.rank, self.world, self.group = rank, world, group
+        self.lo, self.hi, self.n_own = self.halo.lo, self.halo.hi, self.halo.n_own
+        self.edge_ids_cpu = torch.from_numpy(self.halo.edge_ids)
+        local_ei = torch.from_numpy(self.halo.local_edge_index).to(device)
+        self.plan = ops.build_graph_plan(local_ei, self.halo.n_local)
+        self.E_loc = self.plan.E
+        self.exchanger = HaloExchanger(self.halo, device, group)
+
+    def csr_edge_ids(self) -> torch.Tensor:
+        """Global caller edge id stored at each local CSR slot."""
+        return self.edge_ids_cpu.to(self.plan.perm.device)[self.plan.perm.long()]
+
+    def run(self, layers, x_own: torch.Tensor, e_csr: torch.Tensor):
+        layers = list(layers)
+        cfg = layers[0].stack_config()
+        flat = []
+        for layer in layers:
+            s = layer.step_weights(x_own.dtype)
+            flat += [s.w_edge, s.w_node, s.w_proj, s.b_proj]
+        return PartitionedStackFn.apply(cfg, self, x_own, e_csr, *flat)
+
+    def allreduce_grads(self, params) -> None:
+        """Sum of the per-rank partial weight gradients (one flat all-reduce)."""
+        ps = [p for p in params if p.grad is not None]
+        if not ps or self.world == 1:
+            return
+        flat = torch.cat([p.grad.reshape(-1).float() for p in ps])
+        dist.all_reduce(flat, group=self.group)
+        off = 0
+        for p in ps:
+            n = p.numel()
+            p.grad.copy_(flat[off: off + n].view_as(p.grad))
+            off += n

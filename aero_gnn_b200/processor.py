@@ -110,7 +110,7 @@ class MGNStackFn(torch.autograd.Function):
             g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale,
                                                kind="node_bwd")
             agg_eff = agg if scale is None else agg * scale[:, None]
-            g_wn[: D * D] = (g_h0n.float().t() @ agg_eff).reshape(-1)
+            g_wn[: D * D] = (g_h0n.t() @ agg_eff.to(dt)).float().reshape(-1)
             # edge block: total gradient of e' = G_e + g_agg[receiver]
             G_e, g_h0e, g_we = ops.block_bwd(pe, e, P, plan.src, plan.dst, 0, D, G_e, g_agg=g_agg,
                                              has_resid_grad=True, g_main_out=G_e, kind="edge_bwd")
