@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(128) simt_block_bwd_kernel(SimtArgs a) {
 #pragma unroll
   for (int l = 0; l <= MAX_L; ++l) db[l] = 0.f;
   float dgam[4] = {0.f, 0.f, 0.f, 0.f}, dbet[4] = {0.f, 0.f, 0.f, 0.f};
+  float db0 = 0.f;
   const float4 gam4 = *reinterpret_cast<const float4*>(prep_vec(a.prep, L, L + 1) + lane * 4);
   const int act = a.act;
 
@@ -425,6 +426,9 @@ __global__ void __launch_bounds__(128) simt_block_bwd_kernel(SimtArgs a) {
     __syncthreads();
     // Gc = dL/d(pre-activation of h0)
     {
+      float s0 = 0.f;
+      for (int r = 0; r < TM; ++r) s0 += Gc[r * LDS_ + tid];
+      db0 += s0;
       T* gh = reinterpret_cast<T*>(a.g_h0);
       for (int r = w; r < nrows; r += 4) {
         float4 v = *reinterpret_cast<const float4*>(Gc + r * LDS_ + lane * 4);
@@ -456,6 +460,7 @@ __global__ void __launch_bounds__(128) simt_block_bwd_kernel(SimtArgs a) {
   __syncthreads();
   for (int l = 0; l < L; ++l) part[pl.b_hidden(l) + tid] = db[l];
   part[pl.b_out() + tid] = db[L];
+  part[pl.bias0() + tid] = db0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) red[w * 128 + lane * 4 + j] = dgam[j];
   __syncthreads();

@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
   int* sidx = reinterpret_cast<int*>(vec + (L + 3) * 128);                     // [group][2][128]
   float2* red = reinterpret_cast<float2*>(sidx + FWD_GROUPS * 256);            // [group][2][128] LN partials
   uint32_t* segmask = reinterpret_cast<uint32_t*>(red + FWD_GROUPS * 256);     // [group][8]: 4 masks + 2 flags
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(segmask + FWD_GROUPS * 8);
+  int* segs = reinterpret_cast<int*>(segmask + FWD_GROUPS * 8);                // [group][132]: heads + count
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(segs + FWD_GROUPS * 132);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + FWD_GROUPS);
 
   const int tid = threadIdx.x, grp = tid / FWD_GT, gt = tid % FWD_GT, lane = tid & 31;
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
   int* sidx1 = sidx0 + 128;
   float2* gred = red + grp * 256;
   uint32_t* gmask = segmask + grp * 8;
+  int* gseg = segs + grp * 132;
   const int bar_id = 1 + grp;
   uint32_t phase = 0;
   const int act = a.act;
@@ -123,6 +125,19 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
     }
     fence_async_smem();
     named_sync(bar_id, FWD_GT);
+    if (a.agg && gt < 128) {
+      // compact list of segment heads (row numbers) from the ballot masks
+      const uint32_t m0 = gmask[0], m1 = gmask[1], m2 = gmask[2], m3 = gmask[3];
+      const uint32_t mine = gw == 0 ? m0 : (gw == 1 ? m1 : (gw == 2 ? m2 : m3));
+      if ((mine >> lane) & 1u) {
+        int pos = __popc(mine & ((1u << lane) - 1u));
+        if (gw > 0) pos += __popc(m0);
+        if (gw > 1) pos += __popc(m1);
+        if (gw > 2) pos += __popc(m2);
+        gseg[pos] = gt;
+      }
+      if (gt == 0) gseg[128] = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+    }
     // pull this group's next tile into L2 while the current one computes
     {
       const int64_t r = (tile + (int64_t)gridDim.x * FWD_GROUPS) * 128 + (gt >> 1);
@@ -227,30 +242,24 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
         // coalesced store of the output tile
         unstage_rows<FWD_GT>(A, a.out, row0, nrows, gt);
         if (a.agg) {
-          // receiver sums over the bf16-rounded rows: one warp per CSR segment, lane = 4 columns, rows in order
+          // receiver sums over the bf16-rounded rows: one warp per CSR segment (segments k = gw, gw+8, ..),
+          // lane = 4 columns, rows in order
           const uint8_t* base = A + (lane >> 4) * PANEL_BYTES + (lane & 1) * 8;
           const int ch = (lane >> 1) & 7;
           const bool head_open = gmask[4] != 0, tail_open = gmask[5] != 0;
-          int k = 0, prev_start = -1;
-          for (int wd = 0; wd <= 4; ++wd) {
-            uint32_t m = wd < 4 ? gmask[wd] : 1u;   // sentinel closes the last segment
-            while (m) {
-              int start = wd < 4 ? wd * 32 + (__ffs(m) - 1) : nrows;
-              m &= m - 1;
-              if (prev_start >= 0 && ((k - 1) & 7) == gw) {
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int t = prev_start; t < start; ++t) {
-                  uint2 u = *reinterpret_cast<const uint2*>(base + t * 128 + ((ch ^ (t & 7)) << 4));
-                  acc.x += bf16_lo(u.x); acc.y += bf16_hi(u.x); acc.z += bf16_lo(u.y); acc.w += bf16_hi(u.y);
-                }
-                const bool open = (prev_start == 0 && head_open) || (start == nrows && tail_open);
-                float* dst = open ? a.agg_part + ((size_t)tile * 2 + (prev_start == 0 ? 0 : 1)) * 128
-                                  : a.agg + (size_t)sidx1[prev_start] * 128;
-                *reinterpret_cast<float4*>(dst + lane * 4) = acc;
-              }
-              prev_start = start;
-              ++k;
+          const int nseg = gseg[128];
+          for (int k = gw; k < nseg; k += 8) {
+            const int rs = gseg[k];
+            const int re = (k + 1 < nseg) ? gseg[k + 1] : nrows;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int t = rs; t < re; ++t) {
+              uint2 u = *reinterpret_cast<const uint2*>(base + t * 128 + ((ch ^ (t & 7)) << 4));
+              acc.x += bf16_lo(u.x); acc.y += bf16_hi(u.x); acc.z += bf16_lo(u.y); acc.w += bf16_hi(u.y);
             }
+            const bool open = (rs == 0 && head_open) || (re == nrows && tail_open);
+            float* dst = open ? a.agg_part + ((size_t)tile * 2 + (rs == 0 ? 0 : 1)) * 128
+                              : a.agg + (size_t)sidx1[rs] * 128;
+            *reinterpret_cast<float4*>(dst + lane * 4) = acc;
           }
         }
       }
@@ -318,7 +327,7 @@ int umma_prepare(const float* w, int L, void* prepared, cudaStream_t st) {
 
 static size_t fwd_smem(int L) {
   return 1024 + (size_t)(L + 2 + FWD_GROUPS) * TILE_BYTES + (size_t)(L + 3) * 512 +
-         (size_t)FWD_GROUPS * (1024 + 2048 + 32 + 8) + 16;
+         (size_t)FWD_GROUPS * (1024 + 2048 + 32 + 528 + 8) + 16;
 }
 
 size_t umma_block_workspace_bytes(const aero_block_desc* d, int backward) {

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
   float db[UMMA_MAX_L_BWD + 1];
 #pragma unroll
   for (int i = 0; i <= UMMA_MAX_L_BWD; ++i) db[i] = 0.f;
-  float dgam = 0.f, dbet = 0.f;
+  float dgam = 0.f, dbet = 0.f, db0 = 0.f;
 
   const int64_t tiles = (a.rows + 127) / 128;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
         mma_commit(bar_mma);
         if (m + 1 <= L + 1) prefetch(m + 1);   // other slot: last read by GEMM m-1, already complete
       }
-      if (m == 0) dbet += tile_col_sums_512(G, wid, lane);   // d(beta): column sum of the incoming gradient, under the MMA
+      if (m == 0) dbet += tile_col_sums_512(G, wid, lane);   // d(beta): column sums of the incoming gradient, under the MMA
       mbar_wait(bar_mma, phase);
       phase ^= 1;
       fence_after_sync();
@@ -287,7 +287,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
         if (m >= 1) prefetch(m - 1);
       }
       if (m >= 1) db[m - 1] += tile_col_sums_512(Gc, wid, lane);   // bias gradient of Linear m
-      if (m == 0) unstage_rows<BWD_THREADS>(Gc, a.g_h0, row0, nrows, tid);   // g_h0 leaves while the last GEMM runs
+      if (m == 0) {
+        db0 += tile_col_sums_512(Gc, wid, lane);                   // gradient of the first Linear's bias
+        unstage_rows<BWD_THREADS>(Gc, a.g_h0, row0, nrows, tid);   // g_h0 leaves while the last GEMM runs
+      }
       mbar_wait(bar_mma, phase);
       phase ^= 1;
       fence_after_sync();
@@ -367,6 +370,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
     part_out[pl.b_out() + c] = db[L];
     part_out[pl.gamma() + c] = dgam;
     part_out[pl.beta() + c] = dbet;
+    part_out[pl.bias0() + c] = db0;
   }
   __syncthreads();
   if (tid < 32) tmem_dealloc<512>(tmem_base);

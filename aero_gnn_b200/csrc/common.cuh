@@ -149,7 +149,10 @@ struct PackedLayout {
   __host__ __device__ size_t b_out() const { return (size_t)(2 + L) * 16384 + (size_t)L * 128; }
   __host__ __device__ size_t gamma() const { return b_out() + 128; }
   __host__ __device__ size_t beta() const { return b_out() + 256; }
-  __host__ __device__ size_t total() const { return b_out() + 384; }
+  // gradient-only slot: column sums of dL/d(first pre-activation) = gradient of the first Linear's bias, which the
+  // caller folds into P (unused, zero, in the weight vector itself)
+  __host__ __device__ size_t bias0() const { return b_out() + 384; }
+  __host__ __device__ size_t total() const { return b_out() + 512; }
 };
 
 }  // namespace aero

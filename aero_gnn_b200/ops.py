@@ -263,7 +263,7 @@ def segment_bcast(g_out: torch.Tensor, seg_of_row: torch.Tensor, ptr: Optional[t
 # fused block
 # ------------------------------------------------------------------------------------------------
 def packed_floats(L: int) -> int:
-    return (L + 2) * D * D + (L + 3) * D
+    return (L + 2) * D * D + (L + 4) * D   # last D floats: gradient-only slot of the first Linear's bias
 
 
 UMMA_MAX_L = 2

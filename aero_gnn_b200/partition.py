@@ -144,6 +144,7 @@ class PartitionedStackFn(torch.autograd.Function):
             saved += [x, e, agg]
             x, e = x_new, e_new
         ctx.cfg, ctx.part, ctx.K = cfg, part, K
+        ctx.set_materialize_grads(False)
         ctx.paths = (ops.choose_path(x.dtype, cfg.act_edge, cfg.L_edge, backward=True),
                      ops.choose_path(x.dtype, cfg.act_node, cfg.L_node, backward=True))
         ctx.save_for_backward(*saved, *flat)
@@ -157,8 +158,8 @@ class PartitionedStackFn(torch.autograd.Function):
         saved = ctx.saved_tensors
         acts, flat = saved[: 3 * K], saved[3 * K:]
         dt = acts[0].dtype
-        G_x = G_x.contiguous().to(dt)
-        G_e = G_e.contiguous().to(dt).clone()
+        G_x = torch.zeros_like(acts[0]) if G_x is None else G_x.contiguous().to(dt)
+        G_e = torch.zeros_like(acts[1]) if G_e is None else G_e.contiguous().to(dt).clone()
         scale = plan.inv_deg[:n_own].contiguous() if cfg.mean else None
         grads = [None] * (4 * K)
         for k in reversed(range(K)):
@@ -182,7 +183,7 @@ class PartitionedStackFn(torch.autograd.Function):
             g_x.addmm_(g_h0n, w_nx)
             ex.backward(g_ext[n_own:], g_x)
             g_wproj = torch.cat([g_ps.t() @ x_ext, g_pd.t() @ x_ext, g_h0n.t() @ x], dim=0)
-            g_bproj = torch.cat([g_ps.float().sum(0), g_pd.float().sum(0), g_h0n.float().sum(0)]).to(dt)
+            g_bproj = torch.cat([g_we[-D:], g_we[-D:], g_wn[-D:]])
             grads[4 * k: 4 * k + 4] = [g_we, g_wn, g_wproj.to(w_proj.dtype), g_bproj.to(b_proj.dtype)]
             G_x = g_x
         return (None, None, G_x, G_e, *grads)

@@ -47,9 +47,10 @@ class StackConfig:
 
 
 def pack_block(w_main, hidden: Sequence, w_out, b_out, gamma, beta) -> torch.Tensor:
-    """[W_main | W_1..W_L | W_out | b_1..b_L | b_out | gamma | beta] as one fp32 vector."""
+    """[W_main | W_1..W_L | W_out | b_1..b_L | b_out | gamma | beta | 0] as one fp32 vector."""
     parts = [w_main.reshape(-1)] + [w.reshape(-1) for (w, _) in hidden] + [w_out.reshape(-1)]
     parts += [b.reshape(-1) for (_, b) in hidden] + [b_out.reshape(-1), gamma.reshape(-1), beta.reshape(-1)]
+    parts.append(torch.zeros_like(b_out.reshape(-1)))   # gradient-only slot (first Linear's bias lives in b_proj)
     return torch.cat([p.float() for p in parts])
 
 
@@ -84,6 +85,7 @@ class MGNStackFn(torch.autograd.Function):
             saved += [x, e, agg]
             x, e = x_new, e_new
         ctx.cfg, ctx.plan, ctx.K = cfg, plan, K
+        ctx.set_materialize_grads(False)
         ctx.paths = (ops.choose_path(x.dtype, cfg.act_edge, cfg.L_edge, backward=True),
                      ops.choose_path(x.dtype, cfg.act_node, cfg.L_node, backward=True))
         ctx.save_for_backward(*saved, *flat)
@@ -96,8 +98,9 @@ class MGNStackFn(torch.autograd.Function):
         saved = ctx.saved_tensors
         acts, flat = saved[: 3 * K], saved[3 * K:]
         dt = acts[0].dtype
-        G_x = G_x.contiguous().to(dt)
-        G_e = G_e.contiguous().to(dt).clone()
+        G_x = torch.zeros_like(acts[0]) if G_x is None else G_x.contiguous().to(dt)
+        # G_e is updated in place layer by layer; the edge output is usually unused (no gradient materialised)
+        G_e = torch.zeros_like(acts[1]) if G_e is None else G_e.contiguous().to(dt).clone()
         scale = plan.inv_deg if cfg.mean else None
         grads: List[Optional[torch.Tensor]] = [None] * (4 * K)
         for k in reversed(range(K)):
@@ -124,7 +127,8 @@ class MGNStackFn(torch.autograd.Function):
             g_x.addmm_(g_pd, w_d)
             g_x.addmm_(g_h0n, w_nx)
             g_wproj = torch.cat([g_ps.t() @ x, g_pd.t() @ x, g_h0n.t() @ x], dim=0)
-            g_bproj = torch.cat([g_ps.float().sum(0), g_pd.float().sum(0), g_h0n.float().sum(0)]).to(dt)
+            # column sums of g_h0 come out of the block kernels (fp32): sum over edges == sum over senders == receivers
+            g_bproj = torch.cat([g_we[-D:], g_we[-D:], g_wn[-D:]])
             grads[4 * k: 4 * k + 4] = [g_we, g_wn, g_wproj.to(w_proj.dtype), g_bproj.to(b_proj.dtype)]
             G_x = g_x
         return (None, None, G_x, G_e, *grads)
@@ -198,15 +202,15 @@ class SingleBlockFn(torch.autograd.Function):
             g_pd = ops.segment_reduce(g_h0, plan.rowptr, None, plan.N)
             g_x = torch.addmm(g_ps @ w_proj[:D], g_pd, w_proj[D:])
             g_wproj = torch.cat([g_ps.t() @ x, g_pd.t() @ x], dim=0)
-            g_b = torch.cat([g_ps.float().sum(0), g_pd.float().sum(0)]).to(b_proj.dtype)
+            g_b = torch.cat([g_w[-D:], g_w[-D:]]).to(b_proj.dtype)
         else:
             g_agg, g_h0, g_w = ops.block_bwd(prep, agg, P, None, None, 0, 0, g, main_scale=scale)
             agg_eff = agg if scale is None else agg * scale[:, None]
-            g_w[: D * D] = (g_h0.float().t() @ agg_eff).reshape(-1)
+            g_w[: D * D] = (g_h0.t() @ agg_eff.to(dt)).float().reshape(-1)
             g_e = ops.gather_rows(g_agg.to(dt), plan.dst)
             g_x = g_h0 @ w_proj
             g_wproj = g_h0.t() @ x
-            g_b = g_h0.float().sum(0).to(b_proj.dtype)
+            g_b = g_w[-D:].to(b_proj.dtype)
         return (None,) * 6 + (g_e, g_x, g_w, g_wproj.to(w_proj.dtype), g_b)
 
 

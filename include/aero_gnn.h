@@ -131,7 +131,8 @@ int aero_segment_bcast(const void* g_out, const int32_t* seg_of_row, const int32
  *   included, by the caller with a plain GEMM.
  *
  * Packed fp32 weights `w` (floats):  W_main[128*128] | W_1..W_L [L*128*128] | W_out[128*128]
- *                                    | b_1..b_L [L*128] | b_out[128] | gamma[128] | beta[128]
+ *                                    | b_1..b_L [L*128] | b_out[128] | gamma[128] | beta[128] | g_b0[128]
+ * (g_b0: unused in `w`; in `g_w` it receives the gradient of the first Linear's bias = column sums of g_h0)
  * all matrices in nn.Linear layout [out][in].  aero_block_prepare turns them into the image
  * the chosen path reads (SIMT: fp32 + transposes; UMMA: bf16 swizzled shared-memory images).
  * ------------------------------------------------------------------------------------------ */

@@ -56,3 +56,8 @@ def install(reference_root="/root/reference"):
     sys.modules.setdefault("torch_geometric.nn", tgn)
     if reference_root not in sys.path:
         sys.path.insert(0, reference_root)
+    # the reference's `models` directory has no __init__.py (namespace package) and this repository ships a regular
+    # `models` shim package, which would win the import: pin `models` to the reference directory explicitly
+    ref_models = types.ModuleType("models")
+    ref_models.__path__ = [reference_root + "/models"]
+    sys.modules["models"] = ref_models
