@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr", "--extended-lambda",
     "-Xptxas", "-v",
-]
+] + os.environ.get("AERO_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

@@ -46,6 +46,7 @@ __global__ void umma_prepare_kernel(const float* __restrict__ w, int L, uint8_t*
 // =============================================================================================
 // forward
 // =============================================================================================
+template <bool RELU>
 __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
   int* gseg = segs + grp * 132;
   const int bar_id = 1 + grp;
   uint32_t phase = 0;
-  const int act = a.act;
+  const int act = RELU ? AERO_ACT_RELU : a.act;
 
   const int64_t tiles = (a.rows + 127) / 128;
   for (int64_t tile = (int64_t)blockIdx.x * FWD_GROUPS + grp; tile < tiles; tile += (int64_t)gridDim.x * FWD_GROUPS) {
@@ -151,6 +152,16 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
         }
       }
     }
+    // gather indices of the NEXT tile: their pre-projected rows are prefetched into L2 after this tile's first
+    // epilogue, so the layer-0 gathers of the next tile do not pay DRAM latency
+    int nsrc = -1, ndst = -1;
+    {
+      const int64_t r = (tile + (int64_t)gridDim.x * FWD_GROUPS) * 128 + gt;
+      if (gt < 128 && r < a.rows) {
+        nsrc = a.idx0 ? a.idx0[r] : (int)r;
+        ndst = a.idx1 ? a.idx1[r] : -1;
+      }
+    }
 
     for (int layer = 0; layer <= L + 1; ++layer) {
       if (gt == 0) {
@@ -174,6 +185,19 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
         for (int cc = 0; cc < 2; ++cc) hidden_epilogue_chunk(tlane, hf * 2 + cc, p0, p1, bias, act, A, row);
         fence_before_sync();
         fence_async_smem();
+        if (layer == 0 && gt < 128) {
+          if (nsrc >= 0) {
+            const __nv_bfloat16* ps = a.P + (int64_t)nsrc * a.ldp + a.poff0;
+            prefetch_l2(ps);
+            prefetch_l2(ps + 64);
+          }
+          const int pd = __shfl_up_sync(0xffffffffu, ndst, 1);
+          if (ndst >= 0 && (lane == 0 || pd != ndst)) {   // receivers are sorted: one prefetch per distinct row
+            const __nv_bfloat16* pp = a.P + (int64_t)ndst * a.ldp + a.poff1;
+            prefetch_l2(pp);
+            prefetch_l2(pp + 64);
+          }
+        }
         named_sync(bar_id, FWD_GT);
       } else {
         // ---- output epilogue: bias, LayerNorm, residual ----
@@ -351,14 +375,17 @@ int umma_block_fwd(const aero_block_desc* d, cudaStream_t st) {
   if (d->rows == 0) return AERO_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    AERO_CUDA(cudaFuncSetAttribute(umma_block_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    AERO_CUDA(cudaFuncSetAttribute(umma_block_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)fwd_smem(UMMA_MAX_L)));
+    AERO_CUDA(cudaFuncSetAttribute(umma_block_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)fwd_smem(UMMA_MAX_L)));
     attr_set = true;
   }
   int64_t tiles = cdiv(d->rows, 128);
   int64_t want = cdiv(tiles, FWD_GROUPS);
   int grid = (int)(want < sm_count() ? want : sm_count());
-  umma_block_fwd_kernel<<<grid, FWD_THREADS, fwd_smem(d->L), st>>>(a);
+  if (d->act == AERO_ACT_RELU) umma_block_fwd_kernel<true><<<grid, FWD_THREADS, fwd_smem(d->L), st>>>(a);
+  else umma_block_fwd_kernel<false><<<grid, FWD_THREADS, fwd_smem(d->L), st>>>(a);
   AERO_LAUNCH_CHECK();
   if (d->agg) return launch_agg_fixup(a.agg_part, d->rowptr, d->agg, d->rows, d->n_nodes, 128, d->idx1, st);
   return AERO_OK;

@@ -22,8 +22,20 @@ namespace aero {
 
 constexpr int BWD_THREADS = 512;
 
+// Optional phase timing (build with -DAERO_PHASE_TIMING): one observer thread of CTA 0 accumulates clock64 deltas per
+// phase into g_phase[]; read back with aero_debug_phase_read().  Compiled out of the production library.
+#ifdef AERO_PHASE_TIMING
+__device__ long long g_phase[32];
+#define PHASE_INIT() long long _pt = clock64(); const bool _obs = (blockIdx.x == 0 && threadIdx.x == 64)
+#define PHASE(k) do { if (_obs) { long long _n = clock64(); g_phase[k] += _n - _pt; _pt = _n; } } while (0)
+#else
+#define PHASE_INIT() do { } while (0)
+#define PHASE(k) do { } while (0)
+#endif
+
 __device__ __forceinline__ int h_tile(int m) { return m == 0 ? 1 : (m == 1 ? 0 : m); }   // tile holding H_m
 
+template <bool RELU>
 __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
@@ -63,7 +75,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
   const uint32_t w_s = smem_u32(Wslot);
   uint8_t* G = X + (size_t)(NT - 1) * TILE_BYTES;
   const uint32_t g_s = x_s + (uint32_t)(NT - 1) * TILE_BYTES;
-  const int act = a.act;
+  const int act = RELU ? AERO_ACT_RELU : a.act;   // compile-time ReLU: the transcendental paths are not even in the binary
 
   // ---- weight streaming state (used by thread 0 only) ----
   int slot_mat[2] = {-1, -1};
@@ -101,11 +113,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
   float dgam = 0.f, dbet = 0.f, db0 = 0.f;
 
   const int64_t tiles = (a.rows + 127) / 128;
+  PHASE_INIT();
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t row0 = tile * 128;
     const int nrows = (int)((a.rows - row0) < 128 ? (a.rows - row0) : 128);
     const bool valid = row < nrows;
     __syncthreads();   // previous tile fully consumed
+    PHASE(0);
     // ---- stage main rows, gather indices, and the incoming gradient tile (g_out + g_agg[receiver]) ----
     if (a.main_f32) stage_rows<true, BWD_THREADS>(X, a.main, a.main_scale, row0, nrows, tid);
     else stage_rows<false, BWD_THREADS>(X, a.main, nullptr, row0, nrows, tid);
@@ -160,6 +174,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
       }
     }
 
+    // gather indices of the NEXT tile (their rows are prefetched into L2 after the first epilogue below)
+    int nsrc = -1, ndst = -1;
+    {
+      const int64_t r = (tile + gridDim.x) * 128 + tid;
+      if (tid < 128 && r < a.rows) {
+        nsrc = a.idx0 ? a.idx0[r] : (int)r;
+        ndst = a.idx1 ? a.idx1[r] : -1;
+      }
+    }
+    PHASE(1);   // staging
     // ---- forward recompute ----
     for (int m = 0; m <= L + 1; ++m) {
       if (tid == 0) {
@@ -171,9 +195,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
         if (m + 1 <= L + 1) prefetch(m + 1);   // other slot: last read by GEMM m-1, already complete
       }
       if (m == 0) dbet += tile_col_sums_512(G, wid, lane);   // d(beta): column sums of the incoming gradient, under the MMA
+      PHASE(2);   // fwd: issue + column sums
       mbar_wait(bar_mma, phase);
       phase ^= 1;
       fence_after_sync();
+      PHASE(3);   // fwd: wait for MMA
       if (m <= L) {
         uint8_t* Ht = X + (size_t)h_tile(m) * TILE_BYTES;
         const __nv_bfloat16* p0 = nullptr;
@@ -185,9 +211,27 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
         hidden_epilogue_chunk(tlane, ch, p0, p1, m > 0 ? vec + (m - 1) * 128 : nullptr, act, Ht, row);
         fence_before_sync();
         fence_async_smem();
+        if (m == 0 && tid < 128) {
+          if (nsrc >= 0) {
+            const __nv_bfloat16* ps = a.P + (int64_t)nsrc * a.ldp + a.poff0;
+            prefetch_l2(ps);
+            prefetch_l2(ps + 64);
+          }
+          const int pd = __shfl_up_sync(0xffffffffu, ndst, 1);
+          if (ndst >= 0 && (lane == 0 || pd != ndst)) {   // receivers are sorted: one prefetch per distinct row
+            const __nv_bfloat16* pp = a.P + (int64_t)ndst * a.ldp + a.poff1;
+            prefetch_l2(pp);
+            prefetch_l2(pp + 64);
+            if (a.g_agg) {
+              const float* ga = a.g_agg + (size_t)ndst * 128;
+              prefetch_l2(ga); prefetch_l2(ga + 32); prefetch_l2(ga + 64); prefetch_l2(ga + 96);
+            }
+          }
+        }
         __syncthreads();
       }
     }
+    PHASE(4);   // fwd epilogues (+sync)
     // ---- LayerNorm backward; G holds g = dL/d(out) and ends up holding dL/dy ----
     {
       float v[32];
@@ -271,6 +315,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
       fence_async_smem();
       __syncthreads();
     }
+    PHASE(5);   // LayerNorm backward
     // ---- backward through the Linear layers ----
     uint8_t* Gc = G;
     uint32_t gc_s = g_s;
@@ -286,23 +331,30 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
         mma_commit(bar_mma);
         if (m >= 1) prefetch(m - 1);
       }
+      PHASE(14);  // bwd: (thread 0: MMA issue)
       if (m >= 1) db[m - 1] += tile_col_sums_512(Gc, wid, lane);   // bias gradient of Linear m
       if (m == 0) {
         db0 += tile_col_sums_512(Gc, wid, lane);                   // gradient of the first Linear's bias
         unstage_rows<BWD_THREADS>(Gc, a.g_h0, row0, nrows, tid);   // g_h0 leaves while the last GEMM runs
       }
+      PHASE(6);   // bwd: issue + column sums + g_h0 store
       mbar_wait(bar_mma, phase);
       phase ^= 1;
       fence_after_sync();
+      PHASE(7);   // bwd: wait for MMA
       if (m >= 1) {
         uint8_t* Ht = X + (size_t)h_tile(m - 1) * TILE_BYTES;
         float v[32];
         tmem_ld32(tlane + (uint32_t)(ch * 32), v);
+        PHASE(10);  // bwd: tcgen05.ld
         mask_by_act_grad(v, Ht, row, ch, act);
         store_row32(Ht, row, ch, v);   // in place: G_{m-1} over H_{m-1}
+        PHASE(11);  // bwd: mask + pack + store
         fence_before_sync();
         fence_async_smem();
+        PHASE(12);  // bwd: fences
         __syncthreads();
+        PHASE(13);  // bwd: barrier
         Gc = Ht;
         gc_s = x_s + (uint32_t)h_tile(m - 1) * TILE_BYTES;
       } else {
@@ -346,6 +398,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
         }
       }
     }
+    PHASE(8);   // bwd epilogues (+sync)
     first_tile = false;
   }
 
@@ -406,12 +459,15 @@ int umma_block_bwd(const aero_block_desc* d, cudaStream_t st) {
   a.w_part = reinterpret_cast<float*>(d->workspace);
   static bool attr_set = false;
   if (!attr_set) {
-    AERO_CUDA(cudaFuncSetAttribute(umma_block_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    AERO_CUDA(cudaFuncSetAttribute(umma_block_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)bwd_smem(UMMA_MAX_L_BWD)));
+    AERO_CUDA(cudaFuncSetAttribute(umma_block_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)bwd_smem(UMMA_MAX_L_BWD)));
     attr_set = true;
   }
   int grid = bwd_grid_umma(d->rows);
-  umma_block_bwd_kernel<<<grid, BWD_THREADS, bwd_smem(d->L), st>>>(a);
+  if (d->act == AERO_ACT_RELU) umma_block_bwd_kernel<true><<<grid, BWD_THREADS, bwd_smem(d->L), st>>>(a);
+  else umma_block_bwd_kernel<false><<<grid, BWD_THREADS, bwd_smem(d->L), st>>>(a);
   AERO_LAUNCH_CHECK();
   return launch_reduce_partials(a.w_part + off, grid, pl.total(), d->g_w + off, pl.total() - off, st);
 }
@@ -419,3 +475,15 @@ int umma_block_bwd(const aero_block_desc* d, cudaStream_t st) {
 }  // namespace aero
 
 extern "C" int aero_has_umma_bwd(void) { return 1; }
+
+#ifdef AERO_PHASE_TIMING
+extern "C" int aero_debug_phase_read(long long* out_host, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out_host, aero::g_phase, sizeof(long long) * 32);
+  if (reset) {
+    long long z[32] = {0};
+    cudaMemcpyToSymbol(aero::g_phase, z, sizeof(z));
+  }
+  return 0;
+}
+#endif

@@ -9,7 +9,7 @@ import aero_gnn_b200.models as M
 from test_gpu_umma import _grads
 DEV = "cuda:0"
 name = sys.argv[1] if len(sys.argv) > 1 else "layer_sum_L2_add"
-n, e = 300, 2111
+n, e = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (300, 2111)
 g = load_golden(name)
 layer = M.MeshGraphNetLayer(128, 128, 128, **g["kwargs"]); layer.load_state_dict(g["state"])
 layer = layer.to(DEV).to(torch.bfloat16)
@@ -28,3 +28,9 @@ print(f"{'g_x':45s} {rel_l2(gu[0], ref[0]):.4f}      {rel_l2(gs[0], ref[0]):.4f}
 print(f"{'g_e':45s} {rel_l2(gu[1], ref[1]):.4f}      {rel_l2(gs[1], ref[1]):.4f}      {rel_l2(gu[1], gs[1]):.4f}")
 for k, gr in zip(names, ref[2:]):
     print(f"{k:45s} {rel_l2(gu[2][k], gr):.4f}      {rel_l2(gs[2][k], gr):.4f}      {rel_l2(gu[2][k], gs[2][k]):.4f}")
+
+k = "node_block.mlp.layers.0.weight"
+i = names.index(k)
+for nm, sl in (("W_nx", slice(0, 128)), ("W_na", slice(128, 256))):
+    print(nm, "umma-vs-ref", rel_l2(gu[2][k][:, sl], ref[2 + i][:, sl]), "simt-vs-ref", rel_l2(gs[2][k][:, sl], ref[2 + i][:, sl]),
+          "norms", float(ref[2 + i][:, sl].norm()))
