@@ -119,9 +119,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t saddr, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t saddr, uint32_t parity) {
   if (mbar_try_wait(saddr, parity)) return;
   uint32_t spins = 0;
-  while (!mbar_try_wait(saddr, parity)) {
-    __nanosleep(40);
-    if (++spins > (1u << 24)) asm volatile("trap;\n");
+  while (!mbar_try_wait(saddr, parity)) {   // try_wait suspends the warp in hardware until the phase flips or a time limit
+#ifdef AERO_WAIT_NANOSLEEP
+    __nanosleep(AERO_WAIT_NANOSLEEP);
+#endif
+    if (++spins > (1u << 26)) asm volatile("trap;\n");
   }
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }

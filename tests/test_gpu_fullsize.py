@@ -1,0 +1,147 @@
+"""Full-size checks (BASELINE.json configs C3 / C5) through size-independent properties, plus exact equality with
+the numpy oracle where the oracle still finishes in seconds (index work is O(E log E) on the CPU)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mgn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def wing():
+    from aero_gnn_b200.meshes import wing_surface_mesh
+    return wing_surface_mesh(1000, 1000)          # C5: N = 1,000,000, E = 5,996,000
+
+
+def test_c5_graph_plan_properties_and_oracle(wing):
+    from aero_gnn_b200 import ops
+    assert wing.num_nodes == 1_000_000 and wing.num_edges == 5_996_000
+    ei = wing.edge_index.to(DEV)
+    plan = ops.build_graph_plan(ei, wing.num_nodes)
+    E, N = plan.E, plan.N
+    rowptr, perm, src, dst = plan.rowptr.long(), plan.perm.long(), plan.src.long(), plan.dst.long()
+    assert int(rowptr[0]) == 0 and int(rowptr[-1]) == E and bool((rowptr[1:] >= rowptr[:-1]).all())
+    assert bool((dst[1:] >= dst[:-1]).all())                                        # sorted by receiver
+    assert torch.equal(torch.sort(perm).values, torch.arange(E, device=DEV))        # a permutation
+    assert torch.equal(ei[1][perm], dst) and torch.equal(ei[0][perm], src)          # consistent with the input
+    same = dst[1:] == dst[:-1]
+    assert bool((perm[1:][same] > perm[:-1][same]).all())                           # stable inside a receiver
+    deg = torch.bincount(ei[1], minlength=N)
+    assert torch.equal(rowptr[1:] - rowptr[:-1], deg)
+    sperm, sptr = plan.sperm.long(), plan.sptr.long()
+    assert torch.equal(torch.sort(sperm).values, torch.arange(E, device=DEV))
+    ss = src[sperm]
+    assert bool((ss[1:] >= ss[:-1]).all()) and bool((sperm[1:][ss[1:] == ss[:-1]] > sperm[:-1][ss[1:] == ss[:-1]]).all())
+    assert torch.equal(sptr[1:] - sptr[:-1], torch.bincount(ei[0], minlength=N))
+    # exact equality with the numpy oracle (stable argsort) at full size
+    r_rowptr, r_perm, r_src, r_dst, r_sptr, r_sperm = O.receiver_csr(wing.edge_index.numpy(), N)
+    assert np.array_equal(plan.perm.cpu().numpy(), r_perm) and np.array_equal(plan.sperm.cpu().numpy(), r_sperm)
+    assert np.array_equal(plan.rowptr.cpu().numpy(), r_rowptr) and np.array_equal(plan.sptr.cpu().numpy(), r_sptr)
+
+
+def test_c5_segment_reduce_linearity_and_checksum(wing):
+    from aero_gnn_b200 import ops
+    plan = ops.PLAN_CACHE.get(wing.edge_index.to(DEV), wing.num_nodes)
+    g = torch.Generator(device=DEV).manual_seed(0)
+    a = torch.randn(plan.E, 128, device=DEV, generator=g)
+    b = torch.randn(plan.E, 128, device=DEV, generator=g)
+    ra = ops.segment_reduce(a, plan.rowptr, None, plan.N)
+    rb = ops.segment_reduce(b, plan.rowptr, None, plan.N)
+    rab = ops.segment_reduce(a + b, plan.rowptr, None, plan.N)
+    assert float((rab - (ra + rb)).abs().max()) < 1e-4                              # linear
+    assert torch.allclose(ra.double().sum(0), a.double().sum(0), rtol=1e-6, atol=1e-3)   # nothing lost or duplicated
+    rs = ops.segment_reduce(a, plan.sptr, plan.sperm, plan.N)                       # sender-side reduction
+    assert torch.allclose(rs.double().sum(0), a.double().sum(0), rtol=1e-6, atol=1e-3)
+    assert torch.equal(ops.segment_reduce(a, plan.rowptr, None, plan.N), ra)        # deterministic
+
+
+def test_c5_processor_step_deterministic_and_finite(wing):
+    import aero_gnn_b200.models as M
+    from aero_gnn_b200 import ops
+    from aero_gnn_b200.models._common import run_layers
+    torch.manual_seed(0)
+    net = M.MeshGraphNet(6, 4, 5, processor_size=1, num_hidden_layers_node_processor=2,
+                         num_hidden_layers_edge_processor=2, aggregation="add", do_concat_trick=True).to(DEV).to(torch.bfloat16)
+    plan = ops.PLAN_CACHE.get(wing.edge_index.to(DEV), wing.num_nodes)
+    g = torch.Generator().manual_seed(1)
+    x0 = torch.randn(plan.N, 128, generator=g).to(DEV, torch.bfloat16).requires_grad_(True)
+    e0 = torch.randn(plan.E, 128, generator=g).to(DEV, torch.bfloat16).requires_grad_(True)
+    outs = []
+    for _ in range(2):
+        for p in net.layers.parameters():
+            p.grad = None
+        x0.grad = e0.grad = None
+        x, e = run_layers(net.layers, plan, x0, e0)
+        torch.autograd.backward([x, e], [torch.ones_like(x), torch.ones_like(e)])
+        outs.append([x.detach().clone(), e.detach().clone(), x0.grad.clone(), e0.grad.clone()] +
+                    [p.grad.clone() for p in net.layers.parameters()])
+    for a, b in zip(*outs):
+        assert torch.isfinite(a.float()).all() and torch.equal(a, b)
+    # aggregate consistency on a sample: agg of the new edge latents equals a dense scatter of them
+    agg = ops.segment_reduce(outs[0][1], plan.rowptr, None, plan.N, out_dtype=torch.float32)
+    ref = torch.zeros(plan.N, 128, device=DEV).index_add_(0, plan.dst.long(), outs[0][1].float())
+    assert float((agg - ref).abs().max()) < 5e-3
+
+
+def test_c3_bistride_hierarchy_exact_vs_oracle():
+    """C3: 100k-node airfoil mesh, 4 levels, stride 2 -- pooling indices and coarse connectivity of every level equal
+    the numpy restatement of bsms_mgn.py:231-288 exactly."""
+    from aero_gnn_b200 import ops, pooling
+    from aero_gnn_b200.meshes import airfoil_o_mesh
+    mesh = airfoil_o_mesh(400, 250, seed=0)
+    assert mesh.num_nodes == 100_000 and mesh.num_edges == 598_400
+    ei_np, b_np, pos = mesh.edge_index.numpy(), mesh.batch.numpy(), mesh.pos.clone()
+    ei, b, p = mesh.edge_index.to(DEV), mesh.batch.to(DEV), mesh.pos.to(DEV)
+    for level in range(3):
+        lvl = pooling.build_pool_level(ei, b, p, 2)
+        f2c_ref, cb_ref = O.stride_pool_indices(b_np, pos[:, 0].numpy(), 2)
+        cei_ref, inv_ref = O.coarsen_edge_indices(ei_np, f2c_ref, cb_ref.shape[0])
+        assert np.array_equal(lvl.fine_to_coarse.cpu().numpy(), f2c_ref), level
+        assert np.array_equal(lvl.coarse_batch.cpu().numpy(), cb_ref), level
+        assert np.array_equal(lvl.coarse_edge_index.cpu().numpy(), cei_ref), level
+        assert np.array_equal(lvl.inverse.cpu().numpy(), inv_ref), level
+        counts = np.bincount(f2c_ref)
+        assert counts.max() <= 2 and lvl.n_coarse == -(-b_np.shape[0] // 2)
+        key = cei_ref[0] * lvl.n_coarse + cei_ref[1]
+        assert np.all(np.diff(key) > 0)                                             # sorted, unique
+        # next level inputs: mean-pooled positions (bit-exact for stride 2), coarse graph
+        p = ops.segment_reduce(p, lvl.node_gptr, lvl.node_glist, lvl.n_coarse, mean=True)
+        pos = O.scatter_mean(pos, torch.from_numpy(f2c_ref), cb_ref.shape[0])
+        assert torch.equal(p.cpu(), pos), level
+        ei, b = lvl.coarse_edge_index, lvl.coarse_batch
+        ei_np, b_np = cei_ref, cb_ref
+
+
+def test_c2_batched_training_step_bf16_runs_and_matches_fp32():
+    """C2 shape: 8 x 5k-node airfoil meshes, disjoint-union batch, one fwd+bwd of the 15-step MGN in bf16; predictions
+    within 1e-2 (reference RRMSE) of the fp32 path on the same weights."""
+    import aero_gnn_b200.models as M
+    from aero_gnn_b200.meshes import airfoil_o_mesh, batch_meshes
+    from conftest import rrmse
+    mesh = batch_meshes([airfoil_o_mesh(100, 50, seed=s) for s in range(8)])
+    assert mesh.num_nodes == 40_000 and mesh.num_edges == 236_800
+    kw = dict(processor_size=15, num_hidden_layers_node_processor=2, num_hidden_layers_edge_processor=2,
+              num_hidden_layers_node_encoder=2, num_hidden_layers_edge_encoder=2, num_hidden_layers_decoder=2,
+              aggregation="add", do_concat_trick=True)
+    torch.manual_seed(0)
+    net = M.MeshGraphNet(6, 3, 4, **kw).to(DEV)
+    na, ea, ei, tg = mesh.node_attr.to(DEV), mesh.edge_attr.to(DEV), mesh.edge_index.to(DEV), mesh.target.to(DEV)
+    with torch.no_grad():
+        ref = net(na, ea, ei)
+    net16 = net.to(torch.bfloat16)
+    with torch.no_grad():
+        sd16 = {k: v.float() for k, v in net16.state_dict().items()}
+    net32 = M.MeshGraphNet(6, 3, 4, **kw).to(DEV)
+    net32.load_state_dict(sd16)
+    with torch.no_grad():
+        ref16 = net32(na.to(torch.bfloat16).float(), ea.to(torch.bfloat16).float(), ei)   # fp32 path on the bf16-held weights
+    out = net16(na.to(torch.bfloat16), ea.to(torch.bfloat16), ei)
+    loss = torch.nn.functional.mse_loss(out.float(), tg)
+    loss.backward()
+    assert torch.isfinite(loss) and all(torch.isfinite(p.grad.float()).all() for p in net16.parameters())
+    err = rrmse(out.float(), ref16)
+    print("C2 bf16 RRMSE vs fp32 path on bf16-held weights:", err, " vs fp32 weights:", rrmse(out.float(), ref))
+    assert err < 1e-2, err
