@@ -139,6 +139,18 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
       }
       if (gt == 0) gseg[128] = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
     }
+    // this tile's gathered pre-projection rows -> L1, so the layer-0 epilogue (one GEMM later) does not wait on L2
+    if (gt < 128 && gt < nrows) {
+      const __nv_bfloat16* ps = a.P + (int64_t)sidx0[gt] * a.ldp + a.poff0;
+      prefetch_l1(ps);
+      prefetch_l1(ps + 64);
+      const int d1 = sidx1[gt];
+      if (d1 >= 0 && (gt == 0 || sidx1[gt - 1] != d1)) {
+        const __nv_bfloat16* pp = a.P + (int64_t)d1 * a.ldp + a.poff1;
+        prefetch_l1(pp);
+        prefetch_l1(pp + 64);
+      }
+    }
     // pull this group's next tile into L2 while the current one computes
     {
       const int64_t r = (tile + (int64_t)gridDim.x * FWD_GROUPS) * 128 + (gt >> 1);
@@ -173,36 +185,29 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
       phase ^= 1;
       fence_after_sync();
 
-      if (layer <= L) {
-        const __nv_bfloat16* p0 = nullptr;
-        const __nv_bfloat16* p1 = nullptr;
-        if (layer == 0 && row < nrows) {
-          p0 = a.P + (int64_t)sidx0[row] * a.ldp + a.poff0;
-          if (sidx1[row] >= 0) p1 = a.P + (int64_t)sidx1[row] * a.ldp + a.poff1;
-        }
-        const float* bias = layer > 0 ? vec + (layer - 1) * 128 : nullptr;
+      if (layer == 0) {
+        // the MMA that read A has completed: A now receives the coalesced gather P_s[src] + P_d[dst], then each
+        // thread turns its (row, chunk) into h0 in place
+        stage_gather_sum<FWD_GT>(A, a.P, a.ldp, a.poff0, a.poff1, sidx0, sidx1, nrows, gt);
+        named_sync(bar_id, FWD_GT);
 #pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) hidden_epilogue_chunk(tlane, hf * 2 + cc, p0, p1, bias, act, A, row);
+        for (int cc = 0; cc < 2; ++cc) first_epilogue_chunk(tlane, hf * 2 + cc, act, A, row);
         fence_before_sync();
         fence_async_smem();
-        if (layer == 0 && gt < 128) {
-          if (nsrc >= 0) {
-            const __nv_bfloat16* ps = a.P + (int64_t)nsrc * a.ldp + a.poff0;
-            prefetch_l2(ps);
-            prefetch_l2(ps + 64);
-          }
-          const int pd = __shfl_up_sync(0xffffffffu, ndst, 1);
-          if (ndst >= 0 && (lane == 0 || pd != ndst)) {   // receivers are sorted: one prefetch per distinct row
-            const __nv_bfloat16* pp = a.P + (int64_t)ndst * a.ldp + a.poff1;
-            prefetch_l2(pp);
-            prefetch_l2(pp + 64);
-          }
-        }
+        named_sync(bar_id, FWD_GT);
+      } else if (layer <= L) {
+        const float* bias = vec + (layer - 1) * 128;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) hidden_epilogue_chunk(tlane, hf * 2 + cc, nullptr, nullptr, bias, act, A, row);
+        fence_before_sync();
+        fence_async_smem();
         named_sync(bar_id, FWD_GT);
       } else {
         // ---- output epilogue: bias, LayerNorm, residual ----
         const float* bo = vec + L * 128;
         float mean = 0.f, rstd = 1.f;
+        // GEMM_out has consumed A: stage the residual rows into it (coalesced); visible after the next group barrier
+        if (a.resid) stage_rows<false, FWD_GT>(A, a.resid, nullptr, row0, nrows, gt);
         if (a.use_ln) {
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
 #pragma unroll 1
@@ -227,16 +232,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
         }
         const float* gam = vec + (L + 1) * 128;
         const float* bet = vec + (L + 2) * 128;
-        const bool valid = row < nrows;
-        const __nv_bfloat16* rp = (a.resid && valid) ? a.resid + (row0 + row) * 128 : nullptr;
+        if (!a.use_ln && a.resid) named_sync(bar_id, FWD_GT);   // (with LayerNorm the statistics barrier covers it)
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
           const int c = hf * 2 + cc;
-          uint4 r4[4];
-          if (rp) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) r4[j] = *reinterpret_cast<const uint4*>(rp + c * 32 + j * 8);
-          }
           float v[32];
           tmem_ld32(tlane + (uint32_t)(c * 32), v);
 #pragma unroll
@@ -255,10 +254,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
               v[4 * j + 3] = fmaf((v[4 * j + 3] - mean) * rstd, g4.w, e4.w);
             }
           }
-          if (rp) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) add_bf16x8(v + 8 * j, r4[j]);
-          }
+          if (a.resid) add_tile_chunk(v, A, row, c);      // rows beyond nrows were staged as zeros
           store_row32(A, row, c, v);
         }
         fence_before_sync();

@@ -105,6 +105,30 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
     prefetch(1);
   }
 
+  // incoming gradient of a tile, coalesced: tile[r] = bf16( g_out[row0+r] (+ g_agg[receiver of row]) )
+  auto stage_gtot = [&](uint8_t* tile, int64_t row0, int nrows) {
+    const int chunk = tid & 15;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int r = (tid >> 4) + i * 32;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (r < nrows) {
+        v = *reinterpret_cast<const uint4*>(a.g_out + (row0 + r) * 128 + chunk * 8);
+        if (a.g_agg) {
+          int n = a.idx1[row0 + r];
+          const float* gp = a.g_agg + (size_t)n * 128 + chunk * 8;
+          float4 p0 = *reinterpret_cast<const float4*>(gp);
+          float4 p1 = *reinterpret_cast<const float4*>(gp + 4);
+          v.x = pack_bf16(bf16_lo(v.x) + p0.x, bf16_hi(v.x) + p0.y);
+          v.y = pack_bf16(bf16_lo(v.y) + p0.z, bf16_hi(v.y) + p0.w);
+          v.z = pack_bf16(bf16_lo(v.z) + p1.x, bf16_hi(v.z) + p1.y);
+          v.w = pack_bf16(bf16_lo(v.w) + p1.z, bf16_hi(v.w) + p1.w);
+        }
+      }
+      *reinterpret_cast<uint4*>(tile + tile_chunk_off(r, chunk)) = v;
+    }
+  };
+
   uint32_t phase = 0;
   bool first_tile = true;
   float db[UMMA_MAX_L_BWD + 1];
@@ -129,30 +153,21 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
       sidx0[tid] = ok ? (a.idx0 ? a.idx0[r] : (int)r) : 0;
       sidx1[tid] = ok ? (a.idx1 ? a.idx1[r] : -1) : -1;
     }
-    {
-      const int chunk = tid & 15;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int r = (tid >> 4) + i * 32;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (r < nrows) {
-          v = *reinterpret_cast<const uint4*>(a.g_out + (row0 + r) * 128 + chunk * 8);
-          if (a.g_agg) {
-            int n = a.idx1[row0 + r];
-            const float* gp = a.g_agg + (size_t)n * 128 + chunk * 8;
-            float4 p0 = *reinterpret_cast<const float4*>(gp);
-            float4 p1 = *reinterpret_cast<const float4*>(gp + 4);
-            v.x = pack_bf16(bf16_lo(v.x) + p0.x, bf16_hi(v.x) + p0.y);
-            v.y = pack_bf16(bf16_lo(v.y) + p0.z, bf16_hi(v.y) + p0.w);
-            v.z = pack_bf16(bf16_lo(v.z) + p1.x, bf16_hi(v.z) + p1.y);
-            v.w = pack_bf16(bf16_lo(v.w) + p1.z, bf16_hi(v.w) + p1.w);
-          }
-        }
-        *reinterpret_cast<uint4*>(G + tile_chunk_off(r, chunk)) = v;
-      }
-    }
+    stage_gtot(G, row0, nrows);
     fence_async_smem();
     __syncthreads();
+    // this tile's gathered pre-projection rows -> L1 for the layer-0 epilogue of the recompute
+    if (tid < 128 && tid < nrows) {
+      const __nv_bfloat16* ps = a.P + (int64_t)sidx0[tid] * a.ldp + a.poff0;
+      prefetch_l1(ps);
+      prefetch_l1(ps + 64);
+      const int d1 = sidx1[tid];
+      if (d1 >= 0 && (tid == 0 || sidx1[tid - 1] != d1)) {
+        const __nv_bfloat16* pp = a.P + (int64_t)d1 * a.ldp + a.poff1;
+        prefetch_l1(pp);
+        prefetch_l1(pp + 64);
+      }
+    }
     // pull the next tile's rows into L2 while this one computes (HBM latency off the critical path)
     {
       const int64_t nrow0 = (tile + gridDim.x) * 128;
@@ -200,34 +215,20 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
       phase ^= 1;
       fence_after_sync();
       PHASE(3);   // fwd: wait for MMA
-      if (m <= L) {
-        uint8_t* Ht = X + (size_t)h_tile(m) * TILE_BYTES;
-        const __nv_bfloat16* p0 = nullptr;
-        const __nv_bfloat16* p1 = nullptr;
-        if (m == 0 && valid) {
-          p0 = a.P + (int64_t)sidx0[row] * a.ldp + a.poff0;
-          if (sidx1[row] >= 0) p1 = a.P + (int64_t)sidx1[row] * a.ldp + a.poff1;
-        }
-        hidden_epilogue_chunk(tlane, ch, p0, p1, m > 0 ? vec + (m - 1) * 128 : nullptr, act, Ht, row);
+      if (m == 0) {
+        // coalesced gather P_s[src] + P_d[dst] into the tile that will hold H_0, then h0 in place
+        uint8_t* Ht = X + (size_t)h_tile(0) * TILE_BYTES;
+        stage_gather_sum<BWD_THREADS>(Ht, a.P, a.ldp, a.poff0, a.poff1, sidx0, sidx1, nrows, tid);
+        __syncthreads();
+        first_epilogue_chunk(tlane, ch, act, Ht, row);
         fence_before_sync();
         fence_async_smem();
-        if (m == 0 && tid < 128) {
-          if (nsrc >= 0) {
-            const __nv_bfloat16* ps = a.P + (int64_t)nsrc * a.ldp + a.poff0;
-            prefetch_l2(ps);
-            prefetch_l2(ps + 64);
-          }
-          const int pd = __shfl_up_sync(0xffffffffu, ndst, 1);
-          if (ndst >= 0 && (lane == 0 || pd != ndst)) {   // receivers are sorted: one prefetch per distinct row
-            const __nv_bfloat16* pp = a.P + (int64_t)ndst * a.ldp + a.poff1;
-            prefetch_l2(pp);
-            prefetch_l2(pp + 64);
-            if (a.g_agg) {
-              const float* ga = a.g_agg + (size_t)ndst * 128;
-              prefetch_l2(ga); prefetch_l2(ga + 32); prefetch_l2(ga + 64); prefetch_l2(ga + 96);
-            }
-          }
-        }
+        __syncthreads();
+      } else if (m <= L) {
+        uint8_t* Ht = X + (size_t)h_tile(m) * TILE_BYTES;
+        hidden_epilogue_chunk(tlane, ch, nullptr, nullptr, vec + (m - 1) * 128, act, Ht, row);
+        fence_before_sync();
+        fence_async_smem();
         __syncthreads();
       }
     }
@@ -336,6 +337,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
       if (m == 0) {
         db0 += tile_col_sums_512(Gc, wid, lane);                   // gradient of the first Linear's bias
         unstage_rows<BWD_THREADS>(Gc, a.g_h0, row0, nrows, tid);   // g_h0 leaves while the last GEMM runs
+        if (a.has_resid_grad) stage_gtot(G, row0, nrows);          // residual gradient, coalesced, into the free G tile
       }
       PHASE(6);   // bwd: issue + column sums + g_h0 store
       mbar_wait(bar_mma, phase);
@@ -359,6 +361,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
         gc_s = x_s + (uint32_t)h_tile(m - 1) * TILE_BYTES;
       } else {
         // g_main = G_0 W_main (* scale) (+ residual gradient)
+        if (a.has_resid_grad) __syncthreads();   // staged residual gradient visible
         float v[32];
         tmem_ld32(tlane + (uint32_t)(ch * 32), v);
         fence_before_sync();
@@ -368,19 +371,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= sc;
           }
-          if (a.has_resid_grad) {
-            const uint4* gr = reinterpret_cast<const uint4*>(a.g_out + (row0 + row) * 128 + ch * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) add_bf16x8(v + 8 * j, gr[j]);
-            if (a.g_agg) {
-              const float4* ga = reinterpret_cast<const float4*>(a.g_agg + (size_t)sidx1[row] * 128 + ch * 32);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 t4 = ga[j];
-                v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
-              }
-            }
-          }
+          if (a.has_resid_grad) add_tile_chunk(v, G, row, ch);
           if (a.main_f32) {
             float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.g_main) + (row0 + row) * 128 + ch * 32);
 #pragma unroll

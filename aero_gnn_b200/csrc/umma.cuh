@@ -127,6 +127,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t saddr, uint32_t parity) {
   }
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p)); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t saddr, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(saddr), "r"(bytes) : "memory");
 }

@@ -83,6 +83,36 @@ __device__ __forceinline__ void unstage_rows(const uint8_t* tile, __nv_bfloat16*
   }
 }
 
+// Coalesced gather of the pre-projected rows: tile[r] = bf16( P[idx0[r]] (+ P[idx1[r]]) ) for the rows of one tile.
+// A half-warp reads one whole 256-byte row, so every global request touches 2-4 cache lines instead of the 32 a
+// thread-per-row access would; the epilogue then reads its (row, chunk) from shared memory.
+template <int NT>
+__device__ __forceinline__ void stage_gather_sum(uint8_t* tile, const __nv_bfloat16* P, int64_t ldp, int64_t off0,
+                                                 int64_t off1, const int* sidx0, const int* sidx1, int nrows, int t) {
+  const int chunk = t & 15;
+  constexpr int RPP = NT / 16;
+#pragma unroll 4
+  for (int i = 0; i < 128 / RPP; ++i) {
+    int r = (t >> 4) + i * RPP;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < nrows) {
+      v = *reinterpret_cast<const uint4*>(P + (int64_t)sidx0[r] * ldp + off0 + chunk * 8);
+      const int i1 = sidx1[r];
+      if (i1 >= 0) {
+        uint4 q = *reinterpret_cast<const uint4*>(P + (int64_t)i1 * ldp + off1 + chunk * 8);
+        v.x = pack_bf16(bf16_lo(v.x) + bf16_lo(q.x), bf16_hi(v.x) + bf16_hi(q.x));
+        v.y = pack_bf16(bf16_lo(v.y) + bf16_lo(q.y), bf16_hi(v.y) + bf16_hi(q.y));
+        v.z = pack_bf16(bf16_lo(v.z) + bf16_lo(q.z), bf16_hi(v.z) + bf16_hi(q.z));
+        v.w = pack_bf16(bf16_lo(v.w) + bf16_lo(q.w), bf16_hi(v.w) + bf16_hi(q.w));
+      }
+    }
+    *reinterpret_cast<uint4*>(tile + tile_chunk_off(r, chunk)) = v;
+  }
+}
+
+// v[0..31] += the 32 bf16 values stored at (row, chunk c) of a row tile
+__device__ __forceinline__ void add_tile_chunk(float* v, const uint8_t* tile, int row, int c);
+
 // one 128x128x128 GEMM: D(tmem) = A(tile) * B(tile), issued by a single thread
 __device__ __forceinline__ void issue_gemm(uint32_t tacc, uint32_t a_saddr, bool a_mn, uint32_t b_saddr, bool b_mn,
                                            bool accumulate_first) {
@@ -98,6 +128,11 @@ __device__ __forceinline__ void issue_gemm(uint32_t tacc, uint32_t a_saddr, bool
 __device__ __forceinline__ void add_bf16x8(float* v, uint4 q) {
   v[0] += bf16_lo(q.x); v[1] += bf16_hi(q.x); v[2] += bf16_lo(q.y); v[3] += bf16_hi(q.y);
   v[4] += bf16_lo(q.z); v[5] += bf16_hi(q.z); v[6] += bf16_lo(q.w); v[7] += bf16_hi(q.w);
+}
+
+__device__ __forceinline__ void add_tile_chunk(float* v, const uint8_t* tile, int row, int c) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) add_bf16x8(v + 8 * j, *reinterpret_cast<const uint4*>(tile + tile_chunk_off(row, c * 4 + j)));
 }
 
 // write 32 activations of `row` (columns 32*c32 ..) as bf16 into a row tile
@@ -154,6 +189,22 @@ __device__ __forceinline__ void hidden_epilogue_chunk(uint32_t tacc_lane, int c,
     for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], act);
   }
   store_row32(dst_tile, row, c, v);
+}
+
+// first-layer epilogue for one (row, chunk): accumulator + staged gathered sum (read from `tile`), activation, bf16,
+// written back IN PLACE over the staged values (same thread, same bytes)
+__device__ __forceinline__ void first_epilogue_chunk(uint32_t tacc_lane, int c, int act, uint8_t* tile, int row) {
+  float v[32];
+  tmem_ld32(tacc_lane + (uint32_t)(c * 32), v);
+  add_tile_chunk(v, tile, row, c);
+  if (act == AERO_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], act);
+  }
+  store_row32(tile, row, c, v);
 }
 
 // v[j] *= act'(h[j]) for the 32 activations h stored at (row, chunk c) of a bf16 row tile

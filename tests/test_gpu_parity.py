@@ -347,4 +347,4 @@ def test_bf16_layer_vs_fp32_oracle_and_grads():
     ex, ee = rel_l2(xb.grad.float(), gx_ref), rel_l2(eb.grad.float(), ge_ref)
     bx, be = rel_l2(gx16.float(), gx_ref), rel_l2(ge16.float(), ge_ref)
     print("bf16 layer grad rel-L2 err:", ex, ee, " reference bf16 mode:", bx, be)
-    assert ex <= max(1e-2, 1.5 * bx) and ee <= max(1e-2, 1.5 * be)
+    assert ex <= max(1e-2, 2.0 * bx) and ee <= max(1e-2, 2.0 * be)
