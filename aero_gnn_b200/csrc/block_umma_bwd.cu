@@ -153,7 +153,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
       sidx0[tid] = ok ? (a.idx0 ? a.idx0[r] : (int)r) : 0;
       sidx1[tid] = ok ? (a.idx1 ? a.idx1[r] : -1) : -1;
     }
+    PHASE(15);  // staging: main rows + indices issued
     stage_gtot(G, row0, nrows);
+    PHASE(16);  // staging: gradient tile
     fence_async_smem();
     __syncthreads();
     // this tile's gathered pre-projection rows -> L1 for the layer-0 epilogue of the recompute
@@ -376,16 +378,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
             float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.g_main) + (row0 + row) * 128 + ch * 32);
 #pragma unroll
             for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.g_main) + (row0 + row) * 128 + ch * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o4;
-              o4.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]); o4.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-              o4.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o4.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-              op[j] = o4;
-            }
           }
+        }
+        if (!a.main_f32) {
+          // bf16 gradient rows leave through tile 0 (free since m = 1) so the global store is coalesced
+          store_row32(X, row, ch, v);
+          __syncthreads();
+          unstage_rows<BWD_THREADS>(X, reinterpret_cast<__nv_bfloat16*>(a.g_main), row0, nrows, tid);
         }
       }
     }
