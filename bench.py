@@ -294,8 +294,14 @@ def main():
         ab = kernel_alg_bytes(dom, n_rows_E, n_rows_N, b)
         avg_ms = prof[dom]["ms_total"] / max(prof[dom]["count"], 1)
         ach = ab / (avg_ms * 1e-3) / 1e9
+        traffic = None   # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same workload)
+        tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        if world == 1 and os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj["workload"] == {"N": N, "E": E, "dtype": args.dtype} and dom in tj:
+                traffic = tj[dom]["read_bytes"] + tj[dom]["write_bytes"]
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                "peak_source": which, "traffic": None, "avg_ms_per_launch": avg_ms,
+                "peak_source": which, "traffic": traffic, "algorithmic_bytes": ab, "avg_ms_per_launch": avg_ms,
                 "share_of_step": prof[dom]["ms_total"] / (ms * args.steps),
                 "kernels": {k: {"avg_ms": v["ms_total"] / max(v["count"], 1), "share": v["ms_total"] / (ms * args.steps)}
                             for k, v in prof.items()},
