@@ -126,6 +126,11 @@ def cpu_port_step(nu, nv, threads):
     return step, mesh.num_edges, f"wing {nu}x{nv}: N={mesh.num_nodes} E={mesh.num_edges}, fp32, torch CPU autograd"
 
 
+def workload_desc(N, E):
+    return (f"MGN-15 processor fwd+bwd on the synthetic 3-D wing surface mesh (C5): N={N} E={E}, latent 128, L=2, "
+            f"sum-trick edge block, aggregation add")
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -142,8 +147,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "MGN-15 processor edges/sec (fwd+bwd)", "value": val, "unit": "edges/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "MGN-15 processor fwd+bwd, 1M-node/5.996M-edge wing mesh (C5); CPU arm timed on "
-                                   "a bounded sub-mesh of the same generator", "sample": desc},
+            "config": {"workload": workload_desc(args.nu * args.nv, 2 * args.nu * (3 * args.nv - 2)),
+                       "parallelism": "host cores (torch CPU threads)",
+                       "sample": "each step = the same 15-step fwd+bwd on a bounded sub-mesh of the same generator: " + desc},
             "cpu_baseline": {"value": val, "unit": "edges/s", "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -321,8 +327,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "edge_steps_per_s": 15 * value,
-            "config": {"workload": f"MGN-15 processor fwd+bwd on the synthetic 3-D wing surface mesh (C5): "
-                                   f"N={N} E={E}, latent 128, L=2, sum-trick edge block, aggregation add",
+            "config": {"workload": workload_desc(N, E),
                        "parallelism": parallelism, "l2": "inputs (>1.7 GB of latents per step) are larger than L2",
                        "path": "umma" if lib.load().aero_has_umma() and dt == torch.bfloat16 else "simt"},
             "clocks": clocks, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e}
