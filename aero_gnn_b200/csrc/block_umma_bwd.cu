@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
   float* vec = reinterpret_cast<float*>(X + (size_t)NT * TILE_BYTES);
   int* sidx0 = reinterpret_cast<int*>(vec + (L + 3) * 128);
   int* sidx1 = sidx0 + 128;
-  float* red = reinterpret_cast<float*>(sidx1 + 128);          // [4 chunks][128 rows][2]
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 1024);    // [0] mma, [1..2] weight slots
+  float* red = reinterpret_cast<float*>(sidx1 + 128);          // [4 chunks][128 rows] float4 (LayerNorm row sums)
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 2048);    // [0] mma, [1..2] weight slots
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 3);
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -145,17 +145,56 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
     __syncthreads();   // previous tile fully consumed
     PHASE(0);
     // ---- stage main rows, gather indices, and the incoming gradient tile (g_out + g_agg[receiver]) ----
-    if (a.main_f32) stage_rows<true, BWD_THREADS>(X, a.main, a.main_scale, row0, nrows, tid);
-    else stage_rows<false, BWD_THREADS>(X, a.main, nullptr, row0, nrows, tid);
     if (tid < 128) {
       int64_t r = row0 + tid;
       bool ok = tid < nrows;
       sidx0[tid] = ok ? (a.idx0 ? a.idx0[r] : (int)r) : 0;
       sidx1[tid] = ok ? (a.idx1 ? a.idx1[r] : -1) : -1;
     }
-    PHASE(15);  // staging: main rows + indices issued
-    stage_gtot(G, row0, nrows);
-    PHASE(16);  // staging: gradient tile
+    if (a.main_f32) {
+      stage_rows<true, BWD_THREADS>(X, a.main, a.main_scale, row0, nrows, tid);
+      stage_gtot(G, row0, nrows);
+    } else {
+      // edge block: issue every global load of the tile (main rows, incoming gradient rows, receiver ids, then the
+      // receiver gradient rows) before the first shared-memory store, so their latencies overlap
+      const int chunk = tid & 15;
+      uint4 mv[4], gv[4];
+      int dn[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = (tid >> 4) + i * 32;
+        mv[i] = gv[i] = make_uint4(0u, 0u, 0u, 0u);
+        dn[i] = -1;
+        if (r < nrows) {
+          mv[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.main) + (row0 + r) * 128 + chunk * 8);
+          gv[i] = *reinterpret_cast<const uint4*>(a.g_out + (row0 + r) * 128 + chunk * 8);
+          if (a.g_agg) dn[i] = a.idx1[row0 + r];
+        }
+      }
+      float4 ga[4][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        ga[i][0] = ga[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (dn[i] >= 0) {
+          const float* gp = a.g_agg + (size_t)dn[i] * 128 + chunk * 8;
+          ga[i][0] = *reinterpret_cast<const float4*>(gp);
+          ga[i][1] = *reinterpret_cast<const float4*>(gp + 4);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = (tid >> 4) + i * 32;
+        *reinterpret_cast<uint4*>(X + tile_chunk_off(r, chunk)) = mv[i];
+        uint4 v = gv[i];
+        if (dn[i] >= 0) {
+          v.x = pack_bf16(bf16_lo(v.x) + ga[i][0].x, bf16_hi(v.x) + ga[i][0].y);
+          v.y = pack_bf16(bf16_lo(v.y) + ga[i][0].z, bf16_hi(v.y) + ga[i][0].w);
+          v.z = pack_bf16(bf16_lo(v.z) + ga[i][1].x, bf16_hi(v.z) + ga[i][1].y);
+          v.w = pack_bf16(bf16_lo(v.w) + ga[i][1].z, bf16_hi(v.w) + ga[i][1].w);
+        }
+        *reinterpret_cast<uint4*>(G + tile_chunk_off(r, chunk)) = v;
+      }
+    }
     fence_async_smem();
     __syncthreads();
     // this tile's gathered pre-projection rows -> L1 for the layer-0 epilogue of the recompute
@@ -247,72 +286,64 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
         v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
       }
       if (a.use_ln) {
-        float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          s0 += v[j]; s1 += v[j + 1];
-          t0 = fmaf(v[j], v[j], t0); t1 = fmaf(v[j + 1], v[j + 1], t1);
-        }
-        red[(ch * 128 + row) * 2] = s0 + s1;
-        red[(ch * 128 + row) * 2 + 1] = t0 + t1;
-        __syncthreads();
-        float s = 0.f, t = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          s += red[(k * 128 + row) * 2];
-          t += red[(k * 128 + row) * 2 + 1];
-        }
-        const float mean = s * (1.f / 128.f);
-        const float rstd = rsqrtf(fmaxf(t * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
         const float* gam = vec + (L + 1) * 128 + ch * 32;
-        // this thread's 32 gradient values (4 x 16 B of the G tile)
+        // this thread's 32 gradient values (4 x 16 B of the G tile), kept packed
         uint32_t gp[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint4 g4 = *reinterpret_cast<const uint4*>(G + tile_chunk_off(row, ch * 4 + j));
           gp[4 * j] = g4.x; gp[4 * j + 1] = g4.y; gp[4 * j + 2] = g4.z; gp[4 * j + 3] = g4.w;
         }
-        float m1a = 0.f, m1b = 0.f, m2a = 0.f, m2b = 0.f;
-        uint32_t zp[16];
+        // one pass, four row sums: S1 = sum y, S2 = sum y^2, A = sum g*gamma, B = sum g*gamma*y
+        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f, aa = 0.f, ab = 0.f, ba = 0.f, bb = 0.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float glo = bf16_lo(gp[j]), ghi = bf16_hi(gp[j]);
-          float hlo = (v[2 * j] - mean) * rstd, hhi = (v[2 * j + 1] - mean) * rstd;
-          v[2 * j] = hlo;
-          v[2 * j + 1] = hhi;
-          float wlo = glo * gam[2 * j], whi = ghi * gam[2 * j + 1];
-          m1a += wlo; m1b += whi;
-          m2a = fmaf(wlo, hlo, m2a); m2b = fmaf(whi, hhi, m2b);
-          zp[j] = pack_bf16(glo * hlo, ghi * hhi);
+          const float ylo = v[2 * j], yhi = v[2 * j + 1];
+          const float wlo = bf16_lo(gp[j]) * gam[2 * j], whi = bf16_hi(gp[j]) * gam[2 * j + 1];
+          s1a += ylo; s1b += yhi;
+          s2a = fmaf(ylo, ylo, s2a); s2b = fmaf(yhi, yhi, s2b);
+          aa += wlo; ab += whi;
+          ba = fmaf(wlo, ylo, ba); bb = fmaf(whi, yhi, bb);
         }
-        __syncthreads();   // everyone has read the row statistics -> red can be reused
-        red[(ch * 128 + row) * 2] = m1a + m1b;
-        red[(ch * 128 + row) * 2 + 1] = m2a + m2b;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(G + tile_chunk_off(row, ch * 4 + j)) = make_uint4(zp[4 * j], zp[4 * j + 1], zp[4 * j + 2], zp[4 * j + 3]);
+        reinterpret_cast<float4*>(red)[ch * 128 + row] = make_float4(s1a + s1b, s2a + s2b, aa + ab, ba + bb);
         __syncthreads();
-        dgam += tile_col_sums_512(G, wid, lane);   // d(gamma) column sum of z = g * yhat
-        float m1 = 0.f, m2 = 0.f;
+        float S1 = 0.f, S2 = 0.f, A = 0.f, B = 0.f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          m1 += red[(k * 128 + row) * 2];
-          m2 += red[(k * 128 + row) * 2 + 1];
+          const float4 t4 = reinterpret_cast<const float4*>(red)[k * 128 + row];
+          S1 += t4.x; S2 += t4.y; A += t4.z; B += t4.w;
         }
-        m1 *= (1.f / 128.f);
-        m2 *= (1.f / 128.f);
-        __syncthreads();   // z fully consumed
+        const float mean = S1 * (1.f / 128.f);
+        const float rstd = rsqrtf(fmaxf(S2 * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
+        const float m1 = A * (1.f / 128.f);
+        const float m2 = rstd * (B - mean * A) * (1.f / 128.f);   // mean of g*gamma*yhat
+        // dL/dy back into the G tile (same thread, same bytes); z = g*yhat stays in registers for d(gamma)
+        float z[32];
         uint32_t op[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float glo = bf16_lo(gp[j]), ghi = bf16_hi(gp[j]);
-          float olo = rstd * (glo * gam[2 * j] - m1 - v[2 * j] * m2);
-          float ohi = rstd * (ghi * gam[2 * j + 1] - m1 - v[2 * j + 1] * m2);
-          op[j] = pack_bf16(olo, ohi);
+          const float glo = bf16_lo(gp[j]), ghi = bf16_hi(gp[j]);
+          const float hlo = (v[2 * j] - mean) * rstd, hhi = (v[2 * j + 1] - mean) * rstd;
+          z[2 * j] = glo * hlo;
+          z[2 * j + 1] = ghi * hhi;
+          op[j] = pack_bf16(rstd * (glo * gam[2 * j] - m1 - hlo * m2), rstd * (ghi * gam[2 * j + 1] - m1 - hhi * m2));
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           *reinterpret_cast<uint4*>(G + tile_chunk_off(row, ch * 4 + j)) = make_uint4(op[4 * j], op[4 * j + 1], op[4 * j + 2], op[4 * j + 3]);
+        // d(gamma): column sums of z over the warp's 32 rows by a shuffle transpose-reduce (lane l ends with the
+        // sum of column 32*ch + l); fixed order -> deterministic.  No shared memory, no barrier.
+#pragma unroll
+        for (int sft = 16; sft >= 1; sft >>= 1) {
+          const bool upper = (lane & sft) != 0;
+#pragma unroll
+          for (int i = 0; i < sft; ++i) {
+            const float keep = upper ? z[i + sft] : z[i];
+            const float send = upper ? z[i] : z[i + sft];
+            z[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+          }
+        }
+        dgam += z[0];
       }
       // use_ln == 0: dL/dy = g, already in G
       fence_async_smem();
@@ -411,10 +442,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
     const int c = col_of_lane_512(wid, lane);
     for (int l = 0; l < L; ++l) part_out[pl.b_hidden(l) + c] = db[l];
     part_out[pl.b_out() + c] = db[L];
-    part_out[pl.gamma() + c] = dgam;
     part_out[pl.beta() + c] = dbet;
     part_out[pl.bias0() + c] = db0;
   }
+  __syncthreads();
+  red[q * 128 + ch * 32 + lane] = dgam;   // partial over the rows of lane quarter q
+  __syncthreads();
+  if (tid < 128) part_out[pl.gamma() + tid] = (red[tid] + red[128 + tid]) + (red[256 + tid] + red[384 + tid]);
   __syncthreads();
   if (tid < 32) tmem_dealloc<512>(tmem_base);
 }
@@ -422,7 +456,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
 // ---- host side ------------------------------------------------------------------------------------
 static size_t bwd_smem(int L) {
   int nt = (L + 2) > 3 ? (L + 2) : 3;
-  return 1024 + (size_t)(2 + nt) * TILE_BYTES + (size_t)(L + 3) * 512 + 1024 + 4096 + 3 * 8 + 16;
+  return 1024 + (size_t)(2 + nt) * TILE_BYTES + (size_t)(L + 3) * 512 + 1024 + 8192 + 3 * 8 + 16;
 }
 static int bwd_grid_umma(int64_t rows) {
   int64_t tiles = cdiv(rows > 0 ? rows : 1, 128);

@@ -82,7 +82,7 @@ class MGNStackFn(torch.autograd.Function):
             e_new, agg = ops.block_fwd(pe, e, e, P, plan.src, plan.dst, 0, D, rowptr=plan.rowptr, want_agg=True,
                                        kind="edge_fwd")
             x_new, _ = ops.block_fwd(pn, agg, x, P, None, None, 2 * D, 0, main_scale=scale, kind="node_fwd")
-            saved += [x, e, agg]
+            saved += [x, e, agg, P]
             x, e = x_new, e_new
         ctx.cfg, ctx.plan, ctx.K = cfg, plan, K
         ctx.set_materialize_grads(False)
@@ -96,7 +96,7 @@ class MGNStackFn(torch.autograd.Function):
         cfg, plan, K = ctx.cfg, ctx.plan, ctx.K
         path_e, path_n = ctx.paths
         saved = ctx.saved_tensors
-        acts, flat = saved[: 3 * K], saved[3 * K:]
+        acts, flat = saved[: 4 * K], saved[4 * K:]
         dt = acts[0].dtype
         G_x = torch.zeros_like(acts[0]) if G_x is None else G_x.contiguous().to(dt)
         # G_e is updated in place layer by layer; the edge output is usually unused (no gradient materialised)
@@ -104,11 +104,10 @@ class MGNStackFn(torch.autograd.Function):
         scale = plan.inv_deg if cfg.mean else None
         grads: List[Optional[torch.Tensor]] = [None] * (4 * K)
         for k in reversed(range(K)):
-            x, e, agg = acts[3 * k: 3 * k + 3]
+            x, e, agg, P = acts[4 * k: 4 * k + 4]     # P kept from the forward (N x 384 rows: 1/6 of the edge rows)
             w_edge, w_node, w_proj, b_proj = flat[4 * k: 4 * k + 4]
             pe = ops.PreparedBlock(w_edge, cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
             pn = ops.PreparedBlock(w_node, cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
-            P = torch.addmm(b_proj, x, w_proj.t())
             # node block: g_agg, gradient of the node pre-activation, MLP weight grads
             g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale,
                                                kind="node_bwd")
