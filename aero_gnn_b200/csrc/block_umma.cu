@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
   const int q = gw & 3;              // TMEM lane quarter (== warp id % 4)
   const int hf = gw >> 2;            // column half
   const int row = q * 32 + lane;
+  const bool gw0 = __shfl_sync(0xffffffffu, gw, 0) == 0;
   // weights + vectors, once per CTA
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.prep);
@@ -176,10 +177,13 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
     }
 
     for (int layer = 0; layer <= L + 1; ++layer) {
-      if (gt == 0) {
+      if (gw0) {   // first warp of the group, warp-uniform branch; one elected lane issues
         fence_after_sync();
-        issue_gemm(tacc, a_s, false, w_s + (uint32_t)layer * TILE_BYTES, false, false);
-        mma_commit(bar_s);
+        if (elect_one()) {
+          issue_gemm(tacc, a_s, false, w_s + (uint32_t)layer * TILE_BYTES, false, false);
+          mma_commit(bar_s);
+        }
+        __syncwarp();
       }
       mbar_wait(bar_s, phase);
       phase ^= 1;

@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
   const uint32_t g_s = x_s + (uint32_t)(NT - 1) * TILE_BYTES;
   const int act = RELU ? AERO_ACT_RELU : a.act;   // compile-time ReLU: the transcendental paths are not even in the binary
 
-  // ---- weight streaming state (used by thread 0 only) ----
+  // ---- weight streaming + MMA issue belong to warp 0 (a warp-uniform branch; one elected lane touches the hardware) ----
+  const bool w0 = __shfl_sync(0xffffffffu, wid, 0) == 0;
   int slot_mat[2] = {-1, -1};
   bool slot_pending[2] = {false, false};
   uint32_t slot_phase[2] = {0, 0};
@@ -85,8 +86,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
     int s = m & 1;
     if (slot_mat[s] == m) return;
     uint32_t bar = smem_u32(&mbar[1 + s]);
-    mbar_expect_tx(bar, TILE_BYTES);
-    bulk_g2s(w_s + (uint32_t)s * TILE_BYTES, a.prep + (size_t)m * TILE_BYTES, TILE_BYTES, bar);
+    if (elect_one()) {
+      mbar_expect_tx(bar, TILE_BYTES);
+      bulk_g2s(w_s + (uint32_t)s * TILE_BYTES, a.prep + (size_t)m * TILE_BYTES, TILE_BYTES, bar);
+    }
+    __syncwarp();
     slot_mat[s] = m;
     slot_pending[s] = true;
   };
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
     }
     return w_s + (uint32_t)s * TILE_BYTES;
   };
-  if (tid == 0) {
+  if (w0) {
     prefetch(0);
     prefetch(1);
   }
@@ -242,12 +246,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
     PHASE(1);   // staging
     // ---- forward recompute ----
     for (int m = 0; m <= L + 1; ++m) {
-      if (tid == 0) {
+      if (w0) {
         uint32_t wa = acquire(m);
         fence_after_sync();
         uint32_t a_addr = (m == 0) ? x_s : x_s + (uint32_t)h_tile(m - 1) * TILE_BYTES;
-        issue_gemm(tmem_base, a_addr, false, wa, false, false);
-        mma_commit(bar_mma);
+        if (elect_one()) {
+          issue_gemm(tmem_base, a_addr, false, wa, false, false);
+          mma_commit(bar_mma);
+        }
+        __syncwarp();
         if (m + 1 <= L + 1) prefetch(m + 1);   // other slot: last read by GEMM m-1, already complete
       }
       if (m == 0) dbet += tile_col_sums_512(G, wid, lane);   // d(beta): column sums of the incoming gradient, under the MMA
@@ -354,15 +361,18 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
     uint8_t* Gc = G;
     uint32_t gc_s = g_s;
     for (int m = L + 1; m >= 0; --m) {
-      if (tid == 0) {
+      if (w0) {
         uint32_t wa = acquire(m);
         fence_after_sync();
-        if (m >= 1) {
-          uint32_t h_addr = x_s + (uint32_t)h_tile(m - 1) * TILE_BYTES;
-          issue_gemm(tmem_base + (uint32_t)(128 * m), gc_s, true, h_addr, true, !first_tile);   // dW_m += G^T H
+        if (elect_one()) {
+          if (m >= 1) {
+            uint32_t h_addr = x_s + (uint32_t)h_tile(m - 1) * TILE_BYTES;
+            issue_gemm(tmem_base + (uint32_t)(128 * m), gc_s, true, h_addr, true, !first_tile);   // dW_m += G^T H
+          }
+          issue_gemm(tmem_base, gc_s, false, wa, true, false);                                     // G W_m
+          mma_commit(bar_mma);
         }
-        issue_gemm(tmem_base, gc_s, false, wa, true, false);                                     // G W_m
-        mma_commit(bar_mma);
+        __syncwarp();
         if (m >= 1) prefetch(m - 1);
       }
       PHASE(14);  // bwd: (thread 0: MMA issue)

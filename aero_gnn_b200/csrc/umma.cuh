@@ -138,6 +138,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, ui
                : "memory");
 }
 
+// one lane of a fully converged warp; the compiler keeps code under this predicate on the uniform datapath, so the
+// tcgen05.mma operands are built in uniform registers (a `threadIdx.x == 0` branch makes it fall back to a
+// vector-register + R2UR "waterfall" of ~20 dependent instructions per MMA)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(p));
+  return p != 0;
+}
+
 // named barrier for one 128-thread warpgroup
 __device__ __forceinline__ void wg_sync(int id) { asm volatile("bar.sync %0, 128;\n" ::"r"(id) : "memory"); }
 

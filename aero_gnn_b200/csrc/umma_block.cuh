@@ -117,10 +117,18 @@ __device__ __forceinline__ void add_tile_chunk(float* v, const uint8_t* tile, in
 __device__ __forceinline__ void issue_gemm(uint32_t tacc, uint32_t a_saddr, bool a_mn, uint32_t b_saddr, bool b_mn,
                                            bool accumulate_first) {
   const uint32_t idesc = make_idesc(a_mn, b_mn);
+  // descriptors of K-step kk differ from those of step 0 only in the 14-bit start-address field (16-byte units):
+  // K-major +2 per step inside a panel, +1024 for the second panel; MN-major +128 per step
+  const uint64_t ad0 = a_mn ? desc_mnmajor(a_saddr, 0) : desc_kmajor(a_saddr, 0);
+  const uint64_t bd0 = b_mn ? desc_mnmajor(b_saddr, 0) : desc_kmajor(b_saddr, 0);
+  const uint32_t ahi = (uint32_t)(ad0 >> 32), bhi = (uint32_t)(bd0 >> 32);
+  const uint32_t alo = (uint32_t)ad0, blo = (uint32_t)bd0;
 #pragma unroll
   for (int kk = 0; kk < 8; ++kk) {
-    uint64_t ad = a_mn ? desc_mnmajor(a_saddr, kk) : desc_kmajor(a_saddr, kk);
-    uint64_t bd = b_mn ? desc_mnmajor(b_saddr, kk) : desc_kmajor(b_saddr, kk);
+    const uint32_t ka = a_mn ? (uint32_t)kk * 128u : (uint32_t)((kk >> 2) * 1024 + (kk & 3) * 2);
+    const uint32_t kb = b_mn ? (uint32_t)kk * 128u : (uint32_t)((kk >> 2) * 1024 + (kk & 3) * 2);
+    const uint64_t ad = ((uint64_t)ahi << 32) | (uint64_t)(alo + ka);
+    const uint64_t bd = ((uint64_t)bhi << 32) | (uint64_t)(blo + kb);
     mma_bf16(tacc, ad, bd, idesc, accumulate_first || kk > 0);
   }
 }
