@@ -111,24 +111,33 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
 
   // incoming gradient of a tile, coalesced: tile[r] = bf16( g_out[row0+r] (+ g_agg[receiver of row]) )
   auto stage_gtot = [&](uint8_t* tile, int64_t row0, int nrows) {
+    // receiver ids come from the staged index list; every global load is issued before the first shared-memory store
     const int chunk = tid & 15;
+    uint4 gv[4];
+    float4 ga[4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      int r = (tid >> 4) + i * 32;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      const int r = (tid >> 4) + i * 32;
+      gv[i] = make_uint4(0u, 0u, 0u, 0u);
+      ga[i][0] = ga[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < nrows) {
-        v = *reinterpret_cast<const uint4*>(a.g_out + (row0 + r) * 128 + chunk * 8);
-        if (a.g_agg) {
-          int n = a.idx1[row0 + r];
+        gv[i] = *reinterpret_cast<const uint4*>(a.g_out + (row0 + r) * 128 + chunk * 8);
+        const int n = a.g_agg ? sidx1[r] : -1;
+        if (n >= 0) {
           const float* gp = a.g_agg + (size_t)n * 128 + chunk * 8;
-          float4 p0 = *reinterpret_cast<const float4*>(gp);
-          float4 p1 = *reinterpret_cast<const float4*>(gp + 4);
-          v.x = pack_bf16(bf16_lo(v.x) + p0.x, bf16_hi(v.x) + p0.y);
-          v.y = pack_bf16(bf16_lo(v.y) + p0.z, bf16_hi(v.y) + p0.w);
-          v.z = pack_bf16(bf16_lo(v.z) + p1.x, bf16_hi(v.z) + p1.y);
-          v.w = pack_bf16(bf16_lo(v.w) + p1.z, bf16_hi(v.w) + p1.w);
+          ga[i][0] = *reinterpret_cast<const float4*>(gp);
+          ga[i][1] = *reinterpret_cast<const float4*>(gp + 4);
         }
       }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = (tid >> 4) + i * 32;
+      uint4 v = gv[i];
+      v.x = pack_bf16(bf16_lo(v.x) + ga[i][0].x, bf16_hi(v.x) + ga[i][0].y);
+      v.y = pack_bf16(bf16_lo(v.y) + ga[i][0].z, bf16_hi(v.y) + ga[i][0].w);
+      v.z = pack_bf16(bf16_lo(v.z) + ga[i][1].x, bf16_hi(v.z) + ga[i][1].y);
+      v.w = pack_bf16(bf16_lo(v.w) + ga[i][1].z, bf16_hi(v.w) + ga[i][1].w);
       *reinterpret_cast<uint4*>(tile + tile_chunk_off(r, chunk)) = v;
     }
   };
@@ -157,6 +166,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
     }
     if (a.main_f32) {
       stage_rows<true, BWD_THREADS>(X, a.main, a.main_scale, row0, nrows, tid);
+      if (a.g_agg) __syncthreads();   // stage_gtot reads the receiver ids staged just above
       stage_gtot(G, row0, nrows);
     } else {
       // edge block: issue every global load of the tile (main rows, incoming gradient rows, receiver ids, then the
@@ -201,18 +211,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
     }
     fence_async_smem();
     __syncthreads();
-    // this tile's gathered pre-projection rows -> L1 for the layer-0 epilogue of the recompute
-    if (tid < 128 && tid < nrows) {
-      const __nv_bfloat16* ps = a.P + (int64_t)sidx0[tid] * a.ldp + a.poff0;
-      prefetch_l1(ps);
-      prefetch_l1(ps + 64);
-      const int d1 = sidx1[tid];
-      if (d1 >= 0 && (tid == 0 || sidx1[tid - 1] != d1)) {
-        const __nv_bfloat16* pp = a.P + (int64_t)d1 * a.ldp + a.poff1;
-        prefetch_l1(pp);
-        prefetch_l1(pp + 64);
-      }
-    }
     // pull the next tile's rows into L2 while this one computes (HBM latency off the critical path)
     {
       const int64_t nrow0 = (tile + gridDim.x) * 128;
@@ -257,16 +255,20 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
         __syncwarp();
         if (m + 1 <= L + 1) prefetch(m + 1);   // other slot: last read by GEMM m-1, already complete
       }
-      if (m == 0) dbet += tile_col_sums_512(G, wid, lane);   // d(beta): column sums of the incoming gradient, under the MMA
+      if (m == 0) {
+        // under the first MMA: the coalesced gather P_s[src] + P_d[dst] into the (still free) tile that will hold
+        // H_0, and d(beta) = column sums of the incoming gradient
+        stage_gather_sum<BWD_THREADS>(X + (size_t)h_tile(0) * TILE_BYTES, a.P, a.ldp, a.poff0, a.poff1, sidx0, sidx1, nrows, tid);
+        dbet += tile_col_sums_512(G, wid, lane);
+      }
       PHASE(2);   // fwd: issue + column sums
       mbar_wait(bar_mma, phase);
       phase ^= 1;
       fence_after_sync();
       PHASE(3);   // fwd: wait for MMA
       if (m == 0) {
-        // coalesced gather P_s[src] + P_d[dst] into the tile that will hold H_0, then h0 in place
+        // h0 in place over the gathered pre-projection rows
         uint8_t* Ht = X + (size_t)h_tile(0) * TILE_BYTES;
-        stage_gather_sum<BWD_THREADS>(Ht, a.P, a.ldp, a.poff0, a.poff1, sidx0, sidx1, nrows, tid);
         __syncthreads();
         first_epilogue_chunk(tlane, ch, act, Ht, row);
         fence_before_sync();

@@ -91,22 +91,33 @@ __device__ __forceinline__ void stage_gather_sum(uint8_t* tile, const __nv_bfloa
                                                  int64_t off1, const int* sidx0, const int* sidx1, int nrows, int t) {
   const int chunk = t & 15;
   constexpr int RPP = NT / 16;
-#pragma unroll 4
-  for (int i = 0; i < 128 / RPP; ++i) {
-    int r = (t >> 4) + i * RPP;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < nrows) {
-      v = *reinterpret_cast<const uint4*>(P + (int64_t)sidx0[r] * ldp + off0 + chunk * 8);
-      const int i1 = sidx1[r];
-      if (i1 >= 0) {
-        uint4 q = *reinterpret_cast<const uint4*>(P + (int64_t)i1 * ldp + off1 + chunk * 8);
-        v.x = pack_bf16(bf16_lo(v.x) + bf16_lo(q.x), bf16_hi(v.x) + bf16_hi(q.x));
-        v.y = pack_bf16(bf16_lo(v.y) + bf16_lo(q.y), bf16_hi(v.y) + bf16_hi(q.y));
-        v.z = pack_bf16(bf16_lo(v.z) + bf16_lo(q.z), bf16_hi(v.z) + bf16_hi(q.z));
-        v.w = pack_bf16(bf16_lo(v.w) + bf16_lo(q.w), bf16_hi(v.w) + bf16_hi(q.w));
+  // four rows per batch: all eight global loads of a batch are in flight before its first shared-memory store
+#pragma unroll 1
+  for (int b = 0; b < 128 / RPP; b += 4) {
+    uint4 v[4], q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = (t >> 4) + (b + i) * RPP;
+      v[i] = q[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (r < nrows) {
+        v[i] = *reinterpret_cast<const uint4*>(P + (int64_t)sidx0[r] * ldp + off0 + chunk * 8);
+        const int i1 = sidx1[r];
+        if (i1 >= 0) q[i] = *reinterpret_cast<const uint4*>(P + (int64_t)i1 * ldp + off1 + chunk * 8);
       }
     }
-    *reinterpret_cast<uint4*>(tile + tile_chunk_off(r, chunk)) = v;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = (t >> 4) + (b + i) * RPP;
+      const bool two = r < nrows && sidx1[r] >= 0;   // a single operand passes through bit-exactly
+      uint4 o = v[i];
+      if (two) {
+        o.x = pack_bf16(bf16_lo(v[i].x) + bf16_lo(q[i].x), bf16_hi(v[i].x) + bf16_hi(q[i].x));
+        o.y = pack_bf16(bf16_lo(v[i].y) + bf16_lo(q[i].y), bf16_hi(v[i].y) + bf16_hi(q[i].y));
+        o.z = pack_bf16(bf16_lo(v[i].z) + bf16_lo(q[i].z), bf16_hi(v[i].z) + bf16_hi(q[i].z));
+        o.w = pack_bf16(bf16_lo(v[i].w) + bf16_lo(q[i].w), bf16_hi(v[i].w) + bf16_hi(q[i].w));
+      }
+      *reinterpret_cast<uint4*>(tile + tile_chunk_off(r, chunk)) = o;
+    }
   }
 }
 
