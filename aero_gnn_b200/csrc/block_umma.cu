@@ -117,12 +117,15 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
       sidx1[gt] = i1;
       if (a.agg) {
         // receiver-segment heads of this tile (rows are in CSR order) + completeness of the two boundary segments
+        // neighbours across the tile boundary are read straight from the (receiver-sorted) index list: no load
+        // depends on another one
         int prev = __shfl_up_sync(0xffffffffu, i1, 1);
-        if (lane == 0) prev = (gt == 0 || !ok) ? -2 : a.idx1[r - 1];
+        if (lane == 0) prev = (!ok || r == 0) ? -2 : a.idx1[r - 1];
+        const int next = (gt == nrows - 1 && r + 1 < a.rows) ? a.idx1[r + 1] : -2;
         uint32_t m = __ballot_sync(0xffffffffu, ok && (gt == 0 || i1 != prev));
         if (lane == 0) gmask[gw] = m;
-        if (gt == 0) gmask[4] = (a.rowptr[i1] < row0) ? 1u : 0u;                                 // head started earlier
-        if (gt == nrows - 1) gmask[5] = ((int64_t)a.rowptr[i1 + 1] > row0 + nrows) ? 1u : 0u;    // tail continues
+        if (gt == 0) gmask[4] = (prev == i1) ? 1u : 0u;              // head segment started in an earlier tile
+        if (gt == nrows - 1) gmask[5] = (next == i1) ? 1u : 0u;      // tail segment continues in the next tile
       }
     }
     fence_async_smem();

@@ -48,25 +48,49 @@ __device__ __forceinline__ void stage_rows(uint8_t* tile, const void* src, const
                                            int t) {
   const int chunk = t & 15;
   constexpr int RPP = NT / 16;   // rows per pass
-#pragma unroll 4
-  for (int i = 0; i < 128 / RPP; ++i) {
-    int r = (t >> 4) + i * RPP;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < nrows) {
-      if (F32) {
-        const float* p = reinterpret_cast<const float*>(src) + (row0 + r) * 128 + chunk * 8;
-        float4 a = *reinterpret_cast<const float4*>(p);
-        float4 b = *reinterpret_cast<const float4*>(p + 4);
-        float s = scale ? scale[row0 + r] : 1.f;
-        v.x = pack_bf16(a.x * s, a.y * s);
-        v.y = pack_bf16(a.z * s, a.w * s);
-        v.z = pack_bf16(b.x * s, b.y * s);
-        v.w = pack_bf16(b.z * s, b.w * s);
-      } else {
-        v = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src) + (row0 + r) * 128 + chunk * 8);
+  // four rows per batch, every global load of a batch in flight before its first shared-memory store
+#pragma unroll 1
+  for (int b0 = 0; b0 < 128 / RPP; b0 += 4) {
+    if (F32) {
+      float4 a[4], b[4];
+      float s[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = (t >> 4) + (b0 + i) * RPP;
+        a[i] = b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        s[i] = 1.f;
+        if (r < nrows) {
+          const float* p = reinterpret_cast<const float*>(src) + (row0 + r) * 128 + chunk * 8;
+          a[i] = *reinterpret_cast<const float4*>(p);
+          b[i] = *reinterpret_cast<const float4*>(p + 4);
+          if (scale) s[i] = scale[row0 + r];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = (t >> 4) + (b0 + i) * RPP;
+        uint4 v;
+        v.x = pack_bf16(a[i].x * s[i], a[i].y * s[i]);
+        v.y = pack_bf16(a[i].z * s[i], a[i].w * s[i]);
+        v.z = pack_bf16(b[i].x * s[i], b[i].y * s[i]);
+        v.w = pack_bf16(b[i].z * s[i], b[i].w * s[i]);
+        *reinterpret_cast<uint4*>(tile + tile_chunk_off(r, chunk)) = v;
+      }
+    } else {
+      uint4 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = (t >> 4) + (b0 + i) * RPP;
+        v[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (r < nrows)
+          v[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src) + (row0 + r) * 128 + chunk * 8);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = (t >> 4) + (b0 + i) * RPP;
+        *reinterpret_cast<uint4*>(tile + tile_chunk_off(r, chunk)) = v[i];
       }
     }
-    *reinterpret_cast<uint4*>(tile + tile_chunk_off(r, chunk)) = v;
   }
 }
 
@@ -111,10 +135,10 @@ __device__ __forceinline__ void stage_gather_sum(uint8_t* tile, const __nv_bfloa
       const bool two = r < nrows && sidx1[r] >= 0;   // a single operand passes through bit-exactly
       uint4 o = v[i];
       if (two) {
-        o.x = pack_bf16(bf16_lo(v[i].x) + bf16_lo(q[i].x), bf16_hi(v[i].x) + bf16_hi(q[i].x));
-        o.y = pack_bf16(bf16_lo(v[i].y) + bf16_lo(q[i].y), bf16_hi(v[i].y) + bf16_hi(q[i].y));
-        o.z = pack_bf16(bf16_lo(v[i].z) + bf16_lo(q[i].z), bf16_hi(v[i].z) + bf16_hi(q[i].z));
-        o.w = pack_bf16(bf16_lo(v[i].w) + bf16_lo(q[i].w), bf16_hi(v[i].w) + bf16_hi(q[i].w));
+        o.x = add_bf16x2(v[i].x, q[i].x);
+        o.y = add_bf16x2(v[i].y, q[i].y);
+        o.z = add_bf16x2(v[i].z, q[i].z);
+        o.w = add_bf16x2(v[i].w, q[i].w);
       }
       *reinterpret_cast<uint4*>(tile + tile_chunk_off(r, chunk)) = o;
     }
@@ -167,6 +191,19 @@ __device__ __forceinline__ void store_row32(uint8_t* tile, int row, int c32, con
   }
 }
 
+// same, with ReLU fused into the bf16 conversion
+__device__ __forceinline__ void store_row32_relu(uint8_t* tile, int row, int c32, const float* v) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 q;
+    q.x = pack_bf16_relu(v[8 * j + 0], v[8 * j + 1]);
+    q.y = pack_bf16_relu(v[8 * j + 2], v[8 * j + 3]);
+    q.z = pack_bf16_relu(v[8 * j + 4], v[8 * j + 5]);
+    q.w = pack_bf16_relu(v[8 * j + 6], v[8 * j + 7]);
+    *reinterpret_cast<uint4*>(tile + tile_chunk_off(row, c32 * 4 + j)) = q;
+  }
+}
+
 __device__ __forceinline__ float relu_or_act(float v, int act) { return act == AERO_ACT_RELU ? fmaxf(v, 0.f) : act_fwd(v, act); }
 
 // hidden-layer epilogue for one (row, 32-column chunk): accumulator + (gathered pre-projections | bias),
@@ -201,12 +238,11 @@ __device__ __forceinline__ void hidden_epilogue_chunk(uint32_t tacc_lane, int c,
     }
   }
   if (act == AERO_ACT_RELU) {   // uniform branch: the transcendental activations stay out of the hot path
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], act);
+    store_row32_relu(dst_tile, row, c, v);
+    return;
   }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], act);
   store_row32(dst_tile, row, c, v);
 }
 
@@ -217,12 +253,11 @@ __device__ __forceinline__ void first_epilogue_chunk(uint32_t tacc_lane, int c, 
   tmem_ld32(tacc_lane + (uint32_t)(c * 32), v);
   add_tile_chunk(v, tile, row, c);
   if (act == AERO_ACT_RELU) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], act);
+    store_row32_relu(tile, row, c, v);
+    return;
   }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], act);
   store_row32(tile, row, c, v);
 }
 
