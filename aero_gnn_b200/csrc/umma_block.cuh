@@ -107,41 +107,57 @@ __device__ __forceinline__ void unstage_rows(const uint8_t* tile, __nv_bfloat16*
   }
 }
 
+// One batch (rows (t>>4) + (b..b+3) * NT/16) of the gather below, split into its load half and its store half so a
+// caller can keep the loads in flight across a wait.
+template <int NT>
+__device__ __forceinline__ void gather_load4(const __nv_bfloat16* P, int64_t ldp, int64_t off0, int64_t off1,
+                                             const int* sidx0, const int* sidx1, int nrows, int t, int b,
+                                             uint4 (&v)[4], uint4 (&q)[4]) {
+  const int chunk = t & 15;
+  constexpr int RPP = NT / 16;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (t >> 4) + (b + i) * RPP;
+    v[i] = q[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (r < nrows) {
+      v[i] = *reinterpret_cast<const uint4*>(P + (int64_t)sidx0[r] * ldp + off0 + chunk * 8);
+      const int i1 = sidx1[r];
+      if (i1 >= 0) q[i] = *reinterpret_cast<const uint4*>(P + (int64_t)i1 * ldp + off1 + chunk * 8);
+    }
+  }
+}
+template <int NT>
+__device__ __forceinline__ void gather_store4(uint8_t* tile, const int* sidx1, int nrows, int t, int b,
+                                              const uint4 (&v)[4], const uint4 (&q)[4]) {
+  const int chunk = t & 15;
+  constexpr int RPP = NT / 16;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (t >> 4) + (b + i) * RPP;
+    const bool two = r < nrows && sidx1[r] >= 0;   // a single operand passes through bit-exactly
+    uint4 o = v[i];
+    if (two) {
+      o.x = add_bf16x2(v[i].x, q[i].x);
+      o.y = add_bf16x2(v[i].y, q[i].y);
+      o.z = add_bf16x2(v[i].z, q[i].z);
+      o.w = add_bf16x2(v[i].w, q[i].w);
+    }
+    *reinterpret_cast<uint4*>(tile + tile_chunk_off(r, chunk)) = o;
+  }
+}
+
 // Coalesced gather of the pre-projected rows: tile[r] = bf16( P[idx0[r]] (+ P[idx1[r]]) ) for the rows of one tile.
 // A half-warp reads one whole 256-byte row, so every global request touches 2-4 cache lines instead of the 32 a
 // thread-per-row access would; the epilogue then reads its (row, chunk) from shared memory.
 template <int NT>
 __device__ __forceinline__ void stage_gather_sum(uint8_t* tile, const __nv_bfloat16* P, int64_t ldp, int64_t off0,
                                                  int64_t off1, const int* sidx0, const int* sidx1, int nrows, int t) {
-  const int chunk = t & 15;
-  constexpr int RPP = NT / 16;
   // four rows per batch: all eight global loads of a batch are in flight before its first shared-memory store
 #pragma unroll 1
-  for (int b = 0; b < 128 / RPP; b += 4) {
+  for (int b = 0; b < 128 / (NT / 16); b += 4) {
     uint4 v[4], q[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = (t >> 4) + (b + i) * RPP;
-      v[i] = q[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (r < nrows) {
-        v[i] = *reinterpret_cast<const uint4*>(P + (int64_t)sidx0[r] * ldp + off0 + chunk * 8);
-        const int i1 = sidx1[r];
-        if (i1 >= 0) q[i] = *reinterpret_cast<const uint4*>(P + (int64_t)i1 * ldp + off1 + chunk * 8);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = (t >> 4) + (b + i) * RPP;
-      const bool two = r < nrows && sidx1[r] >= 0;   // a single operand passes through bit-exactly
-      uint4 o = v[i];
-      if (two) {
-        o.x = add_bf16x2(v[i].x, q[i].x);
-        o.y = add_bf16x2(v[i].y, q[i].y);
-        o.z = add_bf16x2(v[i].z, q[i].z);
-        o.w = add_bf16x2(v[i].w, q[i].w);
-      }
-      *reinterpret_cast<uint4*>(tile + tile_chunk_off(r, chunk)) = o;
-    }
+    gather_load4<NT>(P, ldp, off0, off1, sidx0, sidx1, nrows, t, b, v, q);
+    gather_store4<NT>(tile, sidx1, nrows, t, b, v, q);
   }
 }
 
