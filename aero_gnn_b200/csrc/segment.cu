@@ -37,14 +37,14 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const T* __restrict__ 
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) segment_reduce_kernel(const TI* __restrict__ in, const int32_t* __restrict__ ptr,
                                                              const int32_t* __restrict__ list, TO* __restrict__ out,
-                                                             int64_t n_seg, int width, int mean) {
+                                                             int64_t n_seg, int width, int64_t ld_out, int mean) {
   int64_t seg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (seg >= n_seg) return;
   int lane = threadIdx.x & 31;
   int b = ptr[seg], e = ptr[seg + 1];
   float scale = 1.f;
   if (mean) scale = 1.f / (float)(e - b > 1 ? e - b : 1);
-  TO* op = out + seg * width;
+  TO* op = out + seg * ld_out;
   if ((width & 3) == 0) {
     for (int c = lane * 4; c < width; c += 128) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -190,28 +190,36 @@ extern "C" int aero_gather_rows(const void* in, const int32_t* idx, const void* 
   return AERO_OK;
 }
 
-extern "C" int aero_segment_reduce(const void* in, const int32_t* ptr, const int32_t* list, void* out, int64_t n_seg,
-                                   int64_t width, int in_dtype, int out_dtype, int mean, void* stream) {
+extern "C" int aero_segment_reduce_ld(const void* in, const int32_t* ptr, const int32_t* list, void* out, int64_t n_seg,
+                                      int64_t width, int64_t ld_out, int in_dtype, int out_dtype, int mean,
+                                      void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   AERO_CHECK_ARG(n_seg >= 0 && width > 0 && width < (1 << 20), "aero_segment_reduce: bad sizes");
+  AERO_CHECK_ARG(ld_out >= width && (((width & 3) != 0) || (ld_out & 3) == 0),
+                 "aero_segment_reduce: ld_out must be >= width (and a multiple of 4 for vector stores)");
   if (n_seg == 0) return AERO_OK;
   AERO_CHECK_ARG(ptr && out, "aero_segment_reduce: null pointer");
   unsigned blocks = (unsigned)cdiv(n_seg, 8);
   int w = (int)width;
   if (in_dtype == AERO_F32 && out_dtype == AERO_F32)
-    segment_reduce_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)in, ptr, list, (float*)out, n_seg, w, mean);
+    segment_reduce_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)in, ptr, list, (float*)out, n_seg, w, ld_out, mean);
   else if (in_dtype == AERO_BF16 && out_dtype == AERO_F32)
-    segment_reduce_kernel<__nv_bfloat16, float><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in, ptr, list, (float*)out, n_seg, w, mean);
+    segment_reduce_kernel<__nv_bfloat16, float><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in, ptr, list, (float*)out, n_seg, w, ld_out, mean);
   else if (in_dtype == AERO_BF16 && out_dtype == AERO_BF16)
-    segment_reduce_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in, ptr, list, (__nv_bfloat16*)out, n_seg, w, mean);
+    segment_reduce_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in, ptr, list, (__nv_bfloat16*)out, n_seg, w, ld_out, mean);
   else if (in_dtype == AERO_F32 && out_dtype == AERO_BF16)
-    segment_reduce_kernel<float, __nv_bfloat16><<<blocks, 256, 0, st>>>((const float*)in, ptr, list, (__nv_bfloat16*)out, n_seg, w, mean);
+    segment_reduce_kernel<float, __nv_bfloat16><<<blocks, 256, 0, st>>>((const float*)in, ptr, list, (__nv_bfloat16*)out, n_seg, w, ld_out, mean);
   else {
     set_error("aero_segment_reduce: unsupported dtypes %d -> %d", in_dtype, out_dtype);
     return AERO_EUNSUPPORTED;
   }
   AERO_LAUNCH_CHECK();
   return AERO_OK;
+}
+
+extern "C" int aero_segment_reduce(const void* in, const int32_t* ptr, const int32_t* list, void* out, int64_t n_seg,
+                                   int64_t width, int in_dtype, int out_dtype, int mean, void* stream) {
+  return aero_segment_reduce_ld(in, ptr, list, out, n_seg, width, width, in_dtype, out_dtype, mean, stream);
 }
 
 extern "C" int aero_segment_bcast(const void* g_out, const int32_t* seg_of_row, const int32_t* ptr, void* g_in,

@@ -49,6 +49,8 @@ SIGNATURES = {
     "aero_hash_u64": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "aero_gather_rows": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
     "aero_segment_reduce": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "aero_segment_reduce_ld": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p]),
     "aero_segment_bcast": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "aero_block_prepared_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "aero_block_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -230,16 +230,22 @@ def gather_rows(inp: torch.Tensor, idx: Optional[torch.Tensor], add: Optional[to
 
 
 def segment_reduce(inp: torch.Tensor, ptr: torch.Tensor, lst: Optional[torch.Tensor], n_seg: int,
-                   mean: bool = False, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-    """out[n] = sum (or mean) of inp[lst[k]] for k in [ptr[n], ptr[n+1]); fixed order, fp32 accumulate."""
+                   mean: bool = False, out_dtype: Optional[torch.dtype] = None,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[n] = sum (or mean) of inp[lst[k]] for k in [ptr[n], ptr[n+1]); fixed order, fp32 accumulate.
+    `out` may be a column block of a wider row-major matrix (unit column stride)."""
     _require_cuda(inp, ptr, lst)
     lib = _l.load()
     inp = inp.contiguous()
     width = inp.size(1)
-    out = torch.empty((n_seg, width), dtype=out_dtype or inp.dtype, device=inp.device)
+    if out is None:
+        out = torch.empty((n_seg, width), dtype=out_dtype or inp.dtype, device=inp.device)
+    elif out.dim() != 2 or out.size(0) != n_seg or out.size(1) != width or out.stride(1) != 1 or not out.is_cuda:
+        raise RuntimeError("segment_reduce: `out` must be a [n_seg, width] CUDA view with unit column stride")
     with torch.cuda.device(inp.device):
-        rc = lib.aero_segment_reduce(_ptr(inp), _ptr(ptr), _ptr(lst), _ptr(out), n_seg, width, dtype_code(inp),
-                                     dtype_code(out), int(mean), _stream())
+        rc = lib.aero_segment_reduce_ld(_ptr(inp), _ptr(ptr), _ptr(lst), _ptr(out), n_seg, width,
+                                        out.stride(0) if n_seg > 1 else max(out.stride(0), width), dtype_code(inp),
+                                        dtype_code(out), int(mean), _stream())
     _l.check(rc, "aero_segment_reduce")
     LaunchCounter.add()
     return out

@@ -118,14 +118,13 @@ class MGNStackFn(torch.autograd.Function):
                                              has_resid_grad=True, g_main_out=G_e, kind="edge_bwd")
             g_we[: D * D] = (g_h0e.t() @ e).float().reshape(-1)
             # gradients of the gathered projections: segmented sums by sender and by receiver
-            g_ps = ops.segment_reduce(g_h0e, plan.sptr, plan.sperm, plan.N)
-            g_pd = ops.segment_reduce(g_h0e, plan.rowptr, None, plan.N)
-            w_s, w_d, w_nx = w_proj[:D], w_proj[D:2 * D], w_proj[2 * D:]
-            g_x = G_x.clone()
-            g_x.addmm_(g_ps, w_s)
-            g_x.addmm_(g_pd, w_d)
-            g_x.addmm_(g_h0n, w_nx)
-            g_wproj = torch.cat([g_ps.t() @ x, g_pd.t() @ x, g_h0n.t() @ x], dim=0)
+            # (both land in one [N, 2D] matrix, so the products with W_s | W_d are single K = 2D GEMMs)
+            g_psd = torch.empty((plan.N, 2 * D), dtype=dt, device=x.device)
+            ops.segment_reduce(g_h0e, plan.sptr, plan.sperm, plan.N, out=g_psd[:, :D])
+            ops.segment_reduce(g_h0e, plan.rowptr, None, plan.N, out=g_psd[:, D:])
+            g_x = torch.addmm(G_x, g_psd, w_proj[:2 * D])
+            g_x.addmm_(g_h0n, w_proj[2 * D:])
+            g_wproj = torch.cat([g_psd.t() @ x, g_h0n.t() @ x], dim=0)
             # column sums of g_h0 come out of the block kernels (fp32): sum over edges == sum over senders == receivers
             g_bproj = torch.cat([g_we[-D:], g_we[-D:], g_wn[-D:]])
             grads[4 * k: 4 * k + 4] = [g_we, g_wn, g_wproj.to(w_proj.dtype), g_bproj.to(b_proj.dtype)]

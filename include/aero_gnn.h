@@ -110,6 +110,11 @@ int aero_gather_rows(const void* in, const int32_t* idx, const void* add, void* 
 int aero_segment_reduce(const void* in, const int32_t* ptr, const int32_t* list, void* out,
                         int64_t n_seg, int64_t width, int in_dtype, int out_dtype, int mean,
                         void* stream);
+/* same, output rows ld_out elements apart (ld_out >= width): lets several reductions fill column blocks of one
+ * matrix, e.g. the [N,256] gradient of the gathered projections P_s | P_d (autograd of mgnLayer.py:40-41,101). */
+int aero_segment_reduce_ld(const void* in, const int32_t* ptr, const int32_t* list, void* out,
+                           int64_t n_seg, int64_t width, int64_t ld_out, int in_dtype, int out_dtype,
+                           int mean, void* stream);
 /* backward of the mean/sum reduce w.r.t. `in`: g_in[i,:] = scale(seg[i]) * g_out[seg[i],:] */
 int aero_segment_bcast(const void* g_out, const int32_t* seg_of_row, const int32_t* ptr,
                        void* g_in, int64_t n_rows, int64_t width, int dtype, int mean, void* stream);
