@@ -57,6 +57,11 @@ class LaunchCounter:
     def add(cls) -> None:
         cls.total += _l.load().aero_last_launch_count()
 
+    @classmethod
+    def bump(cls, n: int) -> None:
+        """Launches replayed by a CUDA graph (graphs.GraphedStep)."""
+        cls.total += int(n)
+
 
 class _Profile:
     """Optional CUDA-event timing of the fused block launches on the launching stream (bench.py roofline)."""

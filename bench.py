@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the processor step as one CUDA graph (auto: only when the mesh is partitioned)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -235,7 +237,33 @@ def main():
     for _ in range(args.warmup):
         proc_step()
     sync_all()
-    ops.PROFILE.reset(enabled=True)
+    # per-kernel CUDA-event split of the step (roofline.kernels): eager, outside the timed region when the timed
+    # region replays a CUDA graph (events cannot be captured), inside it otherwise
+    use_graph = args.graph == "on" or (args.graph == "auto" and world > 1)
+    timed_step, prof, prof_steps, graphed = proc_step, None, args.steps, False
+    if use_graph:
+        ops.PROFILE.reset(enabled=True)
+        proc_step()
+        prof, prof_steps = ops.PROFILE.summary(), 1
+        ops.PROFILE.reset(enabled=False)
+        sync_all()
+        try:
+            from aero_gnn_b200.graphs import GraphedStep
+            timed_step = GraphedStep(proc_step, warmup=1)
+            graphed = True
+            for _ in range(2):
+                timed_step()
+        except Exception as exc:   # noqa: BLE001 -- report and time the eager step instead
+            print(f"[bench] CUDA-graph capture failed on rank {rank}: {exc!r}; timing the eager step", file=sys.stderr)
+            timed_step = proc_step
+        if world > 1:   # every rank must time the same kind of step (a graph replay and an eager step both post the
+            flag = torch.tensor([1 if graphed else 0], device=dev)   # same NCCL operations, so mixing would still run)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                timed_step, graphed = proc_step, False
+        sync_all()
+    else:
+        ops.PROFILE.reset(enabled=True)
     l0 = ops.LaunchCounter.total
     sampler = ClockSampler(local)
     if rank == 0:
@@ -243,13 +271,14 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        proc_step()
+        timed_step()
     ev1.record()
     sync_all()
     ms = ev0.elapsed_time(ev1) / args.steps
     launches = ops.LaunchCounter.total - l0
     clocks = sampler.stop() if rank == 0 else None
-    prof = ops.PROFILE.summary()
+    if prof is None:
+        prof = ops.PROFILE.summary()
     ops.PROFILE.reset(enabled=False)
     if world > 1:
         t = torch.tensor([ms], device=dev)
@@ -285,9 +314,25 @@ def main():
         e2e = {"value": E / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                "ms_per_step": e2e_s * 1e3, "api": "MeshGraphNet.forward + MSELoss + backward (encoders/decoder included)"}
 
+    def shutdown():
+        """Tear the process group down.  Captured graphs that contain NCCL kernels must be released first, and a
+        watchdog bounds the teardown: the result line is already printed, a wedged communicator must not hang the job."""
+        nonlocal timed_step
+        if world <= 1:
+            return
+        dog = threading.Timer(45.0, lambda: os._exit(0))
+        dog.daemon = True
+        dog.start()
+        timed_step = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+        dog.cancel()
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown()
         return
 
     hbm, tc, which = peaks()
@@ -308,8 +353,8 @@ def main():
                 traffic = tj[dom]["read_bytes"] + tj[dom]["write_bytes"]
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                 "peak_source": which, "traffic": traffic, "algorithmic_bytes": ab, "avg_ms_per_launch": avg_ms,
-                "share_of_step": prof[dom]["ms_total"] / (ms * args.steps),
-                "kernels": {k: {"avg_ms": v["ms_total"] / max(v["count"], 1), "share": v["ms_total"] / (ms * args.steps)}
+                "share_of_step": prof[dom]["ms_total"] / (ms * prof_steps),
+                "kernels": {k: {"avg_ms": v["ms_total"] / max(v["count"], 1), "share": v["ms_total"] / (ms * prof_steps)}
                             for k, v in prof.items()},
                 "step_alg_gbytes": alg_bytes_step(E, N, b) / 1e9,
                 "step_frac_hbm": alg_bytes_step(E, N, b) / world / (ms * 1e-3) / 1e9 / hbm}
@@ -329,11 +374,11 @@ def main():
             "edge_steps_per_s": 15 * value,
             "config": {"workload": workload_desc(N, E),
                        "parallelism": parallelism, "l2": "inputs (>1.7 GB of latents per step) are larger than L2",
-                       "path": "umma" if lib.load().aero_has_umma() and dt == torch.bfloat16 else "simt"},
+                       "path": "umma" if lib.load().aero_has_umma() and dt == torch.bfloat16 else "simt",
+                       "launch": "one CUDA graph replay per step" if graphed else "eager launches"},
             "clocks": clocks, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 if __name__ == "__main__":
