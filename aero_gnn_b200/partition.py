@@ -141,7 +141,7 @@ class PartitionedStackFn(torch.autograd.Function):
                                        kind="edge_fwd")
             agg = agg[:n_own]
             x_new, _ = ops.block_fwd(pn, agg, x, P, None, None, 2 * D, 0, main_scale=scale, kind="node_fwd")
-            saved += [x, e, agg]
+            saved += [x_ext, e, agg, P]     # x_ext and P are kept so the backward needs no second halo exchange
             x, e = x_new, e_new
         ctx.cfg, ctx.part, ctx.K = cfg, part, K
         ctx.set_materialize_grads(False)
@@ -156,33 +156,32 @@ class PartitionedStackFn(torch.autograd.Function):
         plan, ex, n_own = part.plan, part.exchanger, part.n_own
         path_e, path_n = ctx.paths
         saved = ctx.saved_tensors
-        acts, flat = saved[: 3 * K], saved[3 * K:]
+        acts, flat = saved[: 4 * K], saved[4 * K:]
         dt = acts[0].dtype
-        G_x = torch.zeros_like(acts[0]) if G_x is None else G_x.contiguous().to(dt)
+        G_x = torch.zeros_like(acts[0][:n_own]) if G_x is None else G_x.contiguous().to(dt)
         G_e = torch.zeros_like(acts[1]) if G_e is None else G_e.contiguous().to(dt).clone()
         scale = plan.inv_deg[:n_own].contiguous() if cfg.mean else None
         grads = [None] * (4 * K)
         for k in reversed(range(K)):
-            x, e, agg = acts[3 * k: 3 * k + 3]
+            x_ext, e, agg, P = acts[4 * k: 4 * k + 4]
+            x = x_ext[:n_own]
             w_edge, w_node, w_proj, b_proj = flat[4 * k: 4 * k + 4]
             pe = ops.PreparedBlock(w_edge, cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
             pn = ops.PreparedBlock(w_node, cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
-            x_ext = torch.cat([x, ex.forward(x)], dim=0)
-            P = torch.addmm(b_proj, x_ext, w_proj.t())
             g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale, kind="node_bwd")
             agg_eff = agg if scale is None else agg * scale[:, None]
             g_wn[: D * D] = (g_h0n.t() @ agg_eff.to(dt)).float().reshape(-1)
             G_e, g_h0e, g_we = ops.block_bwd(pe, e, P, plan.src, plan.dst, 0, D, G_e, g_agg=g_agg, has_resid_grad=True,
                                              g_main_out=G_e, kind="edge_bwd")
             g_we[: D * D] = (g_h0e.t() @ e).float().reshape(-1)
-            g_ps = ops.segment_reduce(g_h0e, plan.sptr, plan.sperm, plan.N)
-            g_pd = ops.segment_reduce(g_h0e, plan.rowptr, None, plan.N)
-            w_s, w_d, w_nx = w_proj[:D], w_proj[D:2 * D], w_proj[2 * D:]
-            g_ext = torch.addmm(g_ps @ w_s, g_pd, w_d)              # [n_local, D]
+            g_psd = torch.empty((plan.N, 2 * D), dtype=dt, device=e.device)   # [g_P_s | g_P_d] over local rows
+            ops.segment_reduce(g_h0e, plan.sptr, plan.sperm, plan.N, out=g_psd[:, :D])
+            ops.segment_reduce(g_h0e, plan.rowptr, None, plan.N, out=g_psd[:, D:])
+            g_ext = g_psd @ w_proj[:2 * D]                          # [n_local, D]
             g_x = G_x + g_ext[:n_own]
-            g_x.addmm_(g_h0n, w_nx)
+            g_x.addmm_(g_h0n, w_proj[2 * D:])
             ex.backward(g_ext[n_own:], g_x)
-            g_wproj = torch.cat([g_ps.t() @ x_ext, g_pd.t() @ x_ext, g_h0n.t() @ x], dim=0)
+            g_wproj = torch.cat([g_psd.t() @ x_ext, g_h0n.t() @ x], dim=0)
             g_bproj = torch.cat([g_we[-D:], g_we[-D:], g_wn[-D:]])
             grads[4 * k: 4 * k + 4] = [g_we, g_wn, g_wproj.to(w_proj.dtype), g_bproj.to(b_proj.dtype)]
             G_x = g_x
