@@ -3,7 +3,8 @@
 Parameter names are the checkpoint contract: `layers.{i}.weight|bias` and `layer_norm.weight|bias`
 (SURVEY.md section 8b).  Inside a processor step the Linear/LayerNorm chain is executed by the fused
 block kernels (processor.py reads the parameters through `split_first` / `tail`); called on its own
-(encoders, decoder -- rows marked "next" in the scope table) it is a dense row-wise chain.
+(encoders) everything after its first Linear runs on the same fused block kernel (processor.DenseTailFn);
+shapes the kernel does not cover (the decoder's narrow output layer) stay a dense row-wise chain of library ops.
 """
 from __future__ import annotations
 
@@ -29,7 +30,26 @@ class MLP(nn.Module):
             self.layer_norm = nn.LayerNorm(output_dim)
         self.dropout = nn.Dropout(dropout)
 
+    def _fusable(self, x: torch.Tensor) -> bool:
+        """Everything after the first Linear can run on the fused block kernel: CUDA rows, 128-wide hidden and
+        output layers, at least one hidden Linear, a supported activation, no active dropout."""
+        from .. import lib as _l
+        from ..ops import D
+        if not (x.is_cuda and x.dim() == 2 and x.size(0) > 0 and x.dtype in (torch.bfloat16, torch.float32)):
+            return False
+        if len(self.layers) < 3 or self.activation_name not in _l.ACT_CODES:
+            return False
+        if self.training and self.dropout.p > 0:
+            return False
+        return all(l.out_features == D for l in self.layers) and all(l.in_features == D for l in self.layers[1:])
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self._fusable(x):
+            from ..processor import dense_tail
+            z = self.layers[0](x)                      # [rows, in] x [in, 128]: a thin library GEMM, bias included
+            hidden, w_out, b_out, gamma, beta = self.tail()
+            return dense_tail(len(hidden), self.activation_name, self.use_layer_norm, z, hidden, w_out, b_out,
+                              gamma, beta)
         last = len(self.layers) - 1
         for i, lin in enumerate(self.layers):
             x = lin(x)

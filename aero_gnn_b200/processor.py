@@ -237,3 +237,57 @@ def node_block_apply(parts: dict, node_attr, edge_attr, edge_index, mean: bool):
     w = pack_block(parts["w_a"], parts["hidden"], parts["w_out"], parts["b_out"], parts["gamma"], parts["beta"])
     return SingleBlockFn.apply("node", len(parts["hidden"]), parts["act"], parts["use_ln"], mean, plan, e_csr, node_attr,
                                w, parts["w_x"].to(dt), parts["b0"].to(dt))
+
+
+# ------------------------------------------------------------------------------------------------
+# standalone MLP (encoders): everything after the first Linear on the fused block kernel
+# ------------------------------------------------------------------------------------------------
+_ZERO_IDX: dict = {}
+_EYE: dict = {}
+
+
+def _zero_idx(rows: int, device) -> torch.Tensor:
+    """int32 zeros [rows]: every row gathers row 0 of the (single-row) pre-projection."""
+    key = (device.index, rows)
+    t = _ZERO_IDX.get(key)
+    if t is None:
+        if len(_ZERO_IDX) > 8:
+            _ZERO_IDX.clear()
+        t = _ZERO_IDX[key] = torch.zeros(rows, dtype=torch.int32, device=device)
+    return t
+
+
+class DenseTailFn(torch.autograd.Function):
+    """out = LN(W_out act(.. act(W_1 act(z) + b_1) ..) + b_out) for z = the first Linear's output, bias included
+    (reference models/mlp.py:40-51 after its first `layer(x)`).  The block kernel's first GEMM runs with
+    W_main = I and a zero pre-projection row, so h_0 = act(z); `w` is the packed vector of pack_block()."""
+
+    @staticmethod
+    def forward(ctx, L: int, act: str, use_ln: bool, z: torch.Tensor, w: torch.Tensor):
+        ops._require_cuda(z, w)
+        z = z.contiguous()
+        P = torch.zeros((1, D), dtype=z.dtype, device=z.device)
+        idx0 = _zero_idx(z.size(0), z.device)
+        prep = ops.PreparedBlock(w.detach(), L, ops.choose_path(z.dtype, act, L), act, use_ln)
+        out, _ = ops.block_fwd(prep, z, None, P, idx0, None, 0, 0, kind="dense_fwd")
+        ctx.meta = (L, act, use_ln, ops.choose_path(z.dtype, act, L, backward=True))
+        ctx.save_for_backward(z, w, P, idx0)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L, act, use_ln, path = ctx.meta
+        z, w, P, idx0 = ctx.saved_tensors
+        prep = ops.PreparedBlock(w, L, path, act, use_ln)
+        # W_main = I: the gradient of the first pre-activation IS the gradient of z (g_main = g_h0 . I is ignored)
+        _, g_h0, g_w = ops.block_bwd(prep, z, P, idx0, None, 0, 0, g.contiguous().to(z.dtype), kind="dense_bwd")
+        return None, None, None, g_h0, g_w
+
+
+def dense_tail(L: int, act: str, use_ln: bool, z: torch.Tensor, hidden: Sequence, w_out, b_out, gamma, beta):
+    key = (z.device.index,)
+    eye = _EYE.get(key)
+    if eye is None:
+        eye = _EYE[key] = torch.eye(D, dtype=torch.float32, device=z.device)
+    w = pack_block(eye, hidden, w_out, b_out, gamma, beta)
+    return DenseTailFn.apply(L, act, use_ln, z, w)

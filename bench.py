@@ -294,25 +294,49 @@ def main():
         h2d = sum(t.numel() * t.element_size() for t in host)
         lossf = torch.nn.MSELoss()
 
-        def e2e_step():
-            na, ea, ei, tg = (t.to(dev, non_blocking=True) for t in host)
+        # Input pipeline as a training loop with a pinned-memory loader runs it: the copy of step i+1's inputs is
+        # issued on a copy stream while step i computes (every step still copies its own 236 MB inside the timed
+        # region and reads its loss back); two device buffers alternate.
+        copy_stream = torch.cuda.Stream()
+        bufs = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        freed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def issue_copy(slot):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[slot])          # the step that last read this buffer has finished
+                for d, h in zip(bufs[slot], host):
+                    d.copy_(h, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        def e2e_step(i):
+            slot = i & 1
+            torch.cuda.current_stream().wait_event(ready[slot])
+            issue_copy(slot ^ 1)                             # next step's inputs travel under this step's compute
+            na, ea, ei, tg = bufs[slot]
             net.zero_grad(set_to_none=True)
             pred = net(na.to(dt), ea.to(dt), ei)
             loss = lossf(pred.float(), tg)
             loss.backward()
+            freed[slot].record()
             return float(loss.item())
 
-        for _ in range(max(1, min(args.warmup, 2))):
-            e2e_step()
+        for ev in freed:
+            ev.record()
+        issue_copy(0)
+        n_warm = max(1, min(args.warmup, 2))
+        for i in range(n_warm):
+            e2e_step(i)
         torch.cuda.synchronize()
         n_e2e = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            e2e_step()
+        for i in range(n_warm, n_warm + n_e2e):
+            e2e_step(i)
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / n_e2e
         e2e = {"value": E / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-               "ms_per_step": e2e_s * 1e3, "api": "MeshGraphNet.forward + MSELoss + backward (encoders/decoder included)"}
+               "ms_per_step": e2e_s * 1e3, "api": "MeshGraphNet.forward + MSELoss + backward (encoders/decoder included)",
+               "input_pipeline": "pinned host -> device on a copy stream, one step ahead (double buffered)"}
 
     def shutdown():
         """Tear the process group down.  Captured graphs that contain NCCL kernels must be released first, and a
