@@ -348,3 +348,55 @@ def test_bf16_layer_vs_fp32_oracle_and_grads():
     bx, be = rel_l2(gx16.float(), gx_ref), rel_l2(ge16.float(), ge_ref)
     print("bf16 layer grad rel-L2 err:", ex, ee, " reference bf16 mode:", bx, be)
     assert ex <= max(1e-2, 2.0 * bx) and ee <= max(1e-2, 2.0 * be)
+
+
+# ---- standalone MLP (encoders): fused tail after the first Linear vs the plain row-wise chain (mlp.py:40-51) ----
+@pytest.mark.parametrize("rows,in_dim,nh,act", [(1, 4, 1, "relu"), (127, 6, 2, "relu"), (1000, 3, 2, "tanh"),
+                                                (4097, 5, 1, "elu")])
+def test_mlp_fused_tail_fp32_vs_chain(rows, in_dim, nh, act):
+    from aero_gnn_b200.models.mlp import MLP
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(rows)
+    mlp = MLP(in_dim, 128, 128, num_hidden_layers=nh, activation_fn=act).to(dev)
+    x = torch.randn(rows, in_dim, device=dev, requires_grad=True)
+    g = torch.randn(rows, 128, device=dev)
+    assert mlp._fusable(x)
+    out = mlp(x)
+    out.backward(g)
+    got = [x.grad.clone()] + [p.grad.clone() for p in mlp.parameters()]
+    x.grad = None
+    mlp.zero_grad(set_to_none=True)
+    h = x                                           # the chain of the reference, fp64 on the same parameters
+    lay = list(mlp.layers)
+    h = h.double()
+    for i, lin in enumerate(lay):
+        h = torch.nn.functional.linear(h, lin.weight.double(), lin.bias.double())
+        if i < len(lay) - 1:
+            h = getattr(torch.nn.functional, act)(h)
+    ref = torch.nn.functional.layer_norm(h, (128,), mlp.layer_norm.weight.double(), mlp.layer_norm.bias.double())
+    ref.backward(g.double())
+    want = [x.grad] + [p.grad for p in mlp.parameters()]
+    assert rel_err(out, ref) < 1e-5, rel_err(out, ref)                 # fp32 tolerance of the north star
+    for a, b in zip(got, want):
+        assert rel_err(a, b) < 1e-4, rel_err(a, b)
+
+
+def test_mlp_fused_tail_bf16_and_unfusable_shapes():
+    from aero_gnn_b200.models.mlp import MLP
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(11)
+    mlp = MLP(6, 128, 128, num_hidden_layers=2).to(dev).to(torch.bfloat16)
+    x = torch.randn(3000, 6, device=dev).to(torch.bfloat16)
+    out = mlp(x)
+    h = x.float()
+    lay = list(mlp.layers)
+    for i, lin in enumerate(lay):
+        h = torch.nn.functional.linear(h, lin.weight.float(), lin.bias.float())
+        if i < len(lay) - 1:
+            h = torch.relu(h)
+    ref = torch.nn.functional.layer_norm(h, (128,), mlp.layer_norm.weight.float(), mlp.layer_norm.bias.float())
+    assert rrmse(out.float(), ref) < 1e-2, rrmse(out.float(), ref)     # bf16 tolerance of the north star
+    # shapes the kernel does not cover stay on the library chain
+    assert not MLP(128, 128, 5, num_hidden_layers=2, use_layer_norm=False).to(dev)._fusable(torch.randn(4, 128, device=dev))
+    assert not MLP(6, 64, 64, num_hidden_layers=2).to(dev)._fusable(torch.randn(4, 6, device=dev))
+    assert not MLP(6, 128, 128, num_hidden_layers=0).to(dev)._fusable(torch.randn(4, 6, device=dev))
