@@ -40,7 +40,11 @@ static int validate_block(const aero_block_desc* d, int backward) {
   AERO_CHECK_ARG(d->rows < 2147483647LL && d->n_nodes < 2147483647LL, "aero_block: sizes exceed int32");
   AERO_CHECK_ARG(d->prepared != nullptr, "aero_block: prepared weights missing");
   if (d->rows > 0) {
-    AERO_CHECK_ARG(d->main && d->P, "aero_block: null main/P");
+    AERO_CHECK_ARG(d->main && (d->P || (backward && d->h0)), "aero_block: null main/P");
+    if (d->h0 && d->path != AERO_PATH_UMMA) {
+      set_error("aero_block: the h0 buffer is supported by AERO_PATH_UMMA only");
+      return AERO_EUNSUPPORTED;
+    }
     AERO_CHECK_ARG((d->ldp % 8) == 0 && (d->poff0 % 8) == 0 && (d->poff1 % 8) == 0, "aero_block: P strides must be multiples of 8");
     if (!backward) AERO_CHECK_ARG(d->out, "aero_block_fwd: null out");  /* resid == NULL: no residual */
     if (!backward && d->agg) AERO_CHECK_ARG(d->rowptr && d->idx1, "aero_block_fwd: agg needs rowptr and idx1 (= receiver)");

@@ -188,6 +188,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
         }
         __syncwarp();
       }
+      if (layer == 1 && a.h0) {
+        // keep h_0 for the backward: the tile is copied out (coalesced) while GEMM 1 reads it; the group barrier
+        // keeps the next epilogue's writes behind the slowest reader and costs nothing under the MMA
+        unstage_rows<FWD_GT>(A, a.h0, row0, nrows, gt);
+        named_sync(bar_id, FWD_GT);
+      }
       mbar_wait(bar_s, phase);
       phase ^= 1;
       fence_after_sync();

@@ -86,6 +86,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
     int s = m & 1;
     if (slot_mat[s] == m) return;
     uint32_t bar = smem_u32(&mbar[1 + s]);
+    if (slot_pending[s]) {   // a transfer nobody waited for: consume its phase before the barrier is re-armed
+      mbar_wait(bar, slot_phase[s]);
+      slot_phase[s] ^= 1;
+      slot_pending[s] = false;
+    }
     if (elect_one()) {
       mbar_expect_tx(bar, TILE_BYTES);
       bulk_g2s(w_s + (uint32_t)s * TILE_BYTES, a.prep + (size_t)m * TILE_BYTES, TILE_BYTES, bar);
@@ -104,9 +109,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
     }
     return w_s + (uint32_t)s * TILE_BYTES;
   };
-  if (w0) {
-    prefetch(0);
-    prefetch(1);
+  if (w0) {   // the first two matrices the recompute needs (layer 0 is skipped when h_0 was kept)
+    const int m0 = a.h0 ? 1 : 0;
+    prefetch(m0);
+    if (m0 + 1 <= L + 1) prefetch(m0 + 1);
   }
 
   // incoming gradient of a tile, coalesced: tile[r] = bf16( g_out[row0+r] (+ g_agg[receiver of row]) )
@@ -164,7 +170,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
       sidx0[tid] = ok ? (a.idx0 ? a.idx0[r] : (int)r) : 0;
       sidx1[tid] = ok ? (a.idx1 ? a.idx1[r] : -1) : -1;
     }
-    if (a.main_f32) {
+    // rows staged for the recompute: `main` into tile 0, or the kept h_0 rows straight into the tile of H_0
+    const bool have_h0 = a.h0 != nullptr;
+    const __nv_bfloat16* rows_bf16 = have_h0 ? a.h0 : reinterpret_cast<const __nv_bfloat16*>(a.main);
+    uint8_t* Rt = have_h0 ? X + (size_t)h_tile(0) * TILE_BYTES : X;
+    if (a.main_f32 && !have_h0) {
       stage_rows<true, BWD_THREADS>(X, a.main, a.main_scale, row0, nrows, tid);
       if (a.g_agg) __syncthreads();   // stage_gtot reads the receiver ids staged just above
       stage_gtot(G, row0, nrows);
@@ -180,7 +190,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
         mv[i] = gv[i] = make_uint4(0u, 0u, 0u, 0u);
         dn[i] = -1;
         if (r < nrows) {
-          mv[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.main) + (row0 + r) * 128 + chunk * 8);
+          mv[i] = *reinterpret_cast<const uint4*>(rows_bf16 + (row0 + r) * 128 + chunk * 8);
           gv[i] = *reinterpret_cast<const uint4*>(a.g_out + (row0 + r) * 128 + chunk * 8);
           if (a.g_agg) dn[i] = a.idx1[row0 + r];
         }
@@ -198,7 +208,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = (tid >> 4) + i * 32;
-        *reinterpret_cast<uint4*>(X + tile_chunk_off(r, chunk)) = mv[i];
+        *reinterpret_cast<uint4*>(Rt + tile_chunk_off(r, chunk)) = mv[i];
         uint4 v = gv[i];
         if (dn[i] >= 0) {
           v.x = pack_bf16(bf16_lo(v.x) + ga[i][0].x, bf16_hi(v.x) + ga[i][0].y);
@@ -219,11 +229,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
         if (r < a.rows) {
           const int part4 = tid & 3;
           if (part4 < 2) {
-            if (a.main_f32) {
+            if (a.main_f32 && !have_h0) {
               prefetch_l2(reinterpret_cast<const float*>(a.main) + r * 128 + part4 * 64);
               prefetch_l2(reinterpret_cast<const float*>(a.main) + r * 128 + part4 * 64 + 32);
             } else {
-              prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(a.main) + r * 128 + part4 * 64);
+              prefetch_l2(rows_bf16 + r * 128 + part4 * 64);
             }
           } else {
             prefetch_l2(a.g_out + r * 128 + (part4 - 2) * 64);
@@ -232,18 +242,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
       }
     }
 
-    // gather indices of the NEXT tile (their rows are prefetched into L2 after the first epilogue below)
-    int nsrc = -1, ndst = -1;
-    {
-      const int64_t r = (tile + gridDim.x) * 128 + tid;
-      if (tid < 128 && r < a.rows) {
-        nsrc = a.idx0 ? a.idx0[r] : (int)r;
-        ndst = a.idx1 ? a.idx1[r] : -1;
-      }
-    }
     PHASE(1);   // staging
-    // ---- forward recompute ----
-    for (int m = 0; m <= L + 1; ++m) {
+    // ---- forward recompute (from layer 1 when h_0 was kept from the forward) ----
+    const int m_first = have_h0 ? 1 : 0;
+    for (int m = m_first; m <= L + 1; ++m) {
       if (w0) {
         uint32_t wa = acquire(m);
         fence_after_sync();
@@ -259,8 +261,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
         // under the first MMA: the coalesced gather P_s[src] + P_d[dst] into the (still free) tile that will hold
         // H_0, and d(beta) = column sums of the incoming gradient
         stage_gather_sum<BWD_THREADS>(X + (size_t)h_tile(0) * TILE_BYTES, a.P, a.ldp, a.poff0, a.poff1, sidx0, sidx1, nrows, tid);
-        dbet += tile_col_sums_512(G, wid, lane);
       }
+      if (m == m_first) dbet += tile_col_sums_512(G, wid, lane);
       PHASE(2);   // fwd: issue + column sums
       mbar_wait(bar_mma, phase);
       phase ^= 1;

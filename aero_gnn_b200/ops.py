@@ -291,6 +291,12 @@ def choose_path(dtype: torch.dtype, act: str, L: int = 0, backward: bool = False
     return _l.AERO_PATH_SIMT
 
 
+def keeps_h0(*paths: int) -> bool:
+    """The first hidden activation is kept from the forward when every kernel of a stack runs on tcgen05
+    (AERO_KEEP_H0=0 switches back to recomputing it, trading 256 B/row of memory for time)."""
+    return os.environ.get("AERO_KEEP_H0", "1") != "0" and all(p == _l.AERO_PATH_UMMA for p in paths)
+
+
 class PreparedBlock:
     """Device image of one block's weights for a kernel path (rebuilt when the weights change)."""
 
@@ -312,22 +318,29 @@ class PreparedBlock:
         LaunchCounter.add()
 
 
-def _desc(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, main_scale=None, rowptr=None, n_nodes=0):
+def _desc(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, main_scale=None, rowptr=None, n_nodes=0,
+          like=None):
+    """`P` may be None in a backward that reads the kept h_0 rows (`like` then gives the latent dtype)."""
     d = _l.BlockDesc()
-    d.dtype = dtype_code(P)
+    if P is None:
+        P_dtype, P_ptr, ldp = like.dtype, None, 0
+        d.dtype = dtype_code(like)
+    else:
+        P_dtype, P_ptr, ldp = P.dtype, P.data_ptr(), P.size(1)
+        d.dtype = dtype_code(P)
     d.path = prep.path
     d.L = prep.L
     d.act = prep.act
     d.use_ln = prep.use_ln
-    d.main_f32 = int(main.dtype == torch.float32 and P.dtype != torch.float32)
+    d.main_f32 = int(main.dtype == torch.float32 and P_dtype != torch.float32)
     d.rows = main.size(0)
     d.n_nodes = n_nodes
-    d.ldp = P.size(1)
+    d.ldp = ldp
     d.poff0, d.poff1 = poff0, poff1
     d.main = main.data_ptr()
     d.main_scale = main_scale.data_ptr() if main_scale is not None else None
     d.resid = resid.data_ptr() if resid is not None else None
-    d.P = P.data_ptr()
+    d.P = P_ptr
     d.idx0 = idx0.data_ptr() if idx0 is not None else None
     d.idx1 = idx1.data_ptr() if idx1 is not None else None
     d.rowptr = rowptr.data_ptr() if rowptr is not None else None
@@ -336,8 +349,9 @@ def _desc(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, main
 
 
 def block_fwd(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, main_scale=None, rowptr=None,
-              want_agg=False, kind=None):
-    """Forward of one fused block; returns (out, agg or None)."""
+              want_agg=False, kind=None, h0_out: Optional[torch.Tensor] = None):
+    """Forward of one fused block; returns (out, agg or None).  `h0_out` ([rows,128], latent dtype, tcgen05 path
+    only) receives the first hidden activation so that the backward does not have to recompute it."""
     _require_cuda(main, resid, P)
     lib = _l.load()
     n_nodes = P.size(0)
@@ -346,6 +360,7 @@ def block_fwd(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, 
     agg = torch.empty((n_nodes, D), dtype=torch.float32, device=P.device) if want_agg else None
     d.out = out.data_ptr()
     d.agg = agg.data_ptr() if agg is not None else None
+    d.h0 = h0_out.data_ptr() if h0_out is not None else None
     ws = _workspace(lib.aero_block_workspace_bytes(C.byref(d), 0), P.device)
     d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
     tok = PROFILE.begin(kind)
@@ -358,25 +373,33 @@ def block_fwd(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, 
 
 
 def block_bwd(prep: PreparedBlock, main, P, idx0, idx1, poff0, poff1, g_out, *, g_agg=None, main_scale=None,
-              has_resid_grad=False, g_main_out: Optional[torch.Tensor] = None, kind=None):
-    """Backward of one fused block; returns (g_main, g_h0, g_w_packed[fp32], W_main slot zero)."""
-    _require_cuda(main, P, g_out)
+              has_resid_grad=False, g_main_out: Optional[torch.Tensor] = None, kind=None,
+              h0: Optional[torch.Tensor] = None, n_nodes: Optional[int] = None):
+    """Backward of one fused block; returns (g_main, g_h0, g_w_packed[fp32], W_main slot zero).  With `h0` (the
+    rows kept by block_fwd(h0_out=...)) layer 0 is not recomputed and `P` may be None."""
+    _require_cuda(main, P, g_out, h0)
     lib = _l.load()
-    d = _desc(prep, main, None, P, idx0, idx1, poff0, poff1, main_scale=main_scale, n_nodes=P.size(0))
+    if P is None and h0 is None:
+        raise RuntimeError("block_bwd needs the pre-projection P or the kept h_0 rows")
+    dev, ldt = g_out.device, g_out.dtype
+    if n_nodes is None:
+        n_nodes = P.size(0) if P is not None else (g_agg.size(0) if g_agg is not None else main.size(0))
+    d = _desc(prep, main, None, P, idx0, idx1, poff0, poff1, main_scale=main_scale, n_nodes=n_nodes, like=g_out)
+    d.h0 = h0.data_ptr() if h0 is not None else None
     rows = main.size(0)
-    g_main = g_main_out if g_main_out is not None else torch.empty((rows, D), dtype=main.dtype, device=P.device)
-    g_h0 = torch.empty((rows, D), dtype=P.dtype, device=P.device)
-    g_w = torch.zeros(packed_floats(prep.L), dtype=torch.float32, device=P.device)
+    g_main = g_main_out if g_main_out is not None else torch.empty((rows, D), dtype=main.dtype, device=dev)
+    g_h0 = torch.empty((rows, D), dtype=ldt, device=dev)
+    g_w = torch.zeros(packed_floats(prep.L), dtype=torch.float32, device=dev)
     d.has_resid_grad = int(has_resid_grad)
     d.g_out = g_out.data_ptr()
     d.g_agg = g_agg.data_ptr() if g_agg is not None else None
     d.g_main = g_main.data_ptr()
     d.g_h0 = g_h0.data_ptr()
     d.g_w = g_w.data_ptr()
-    ws = _workspace(lib.aero_block_workspace_bytes(C.byref(d), 1), P.device)
+    ws = _workspace(lib.aero_block_workspace_bytes(C.byref(d), 1), dev)
     d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
     tok = PROFILE.begin(kind)
-    with torch.cuda.device(P.device):
+    with torch.cuda.device(dev):
         rc = lib.aero_block_bwd(C.byref(d), _stream())
     PROFILE.end(tok)
     _l.check(rc, "aero_block_bwd")

@@ -130,6 +130,9 @@ class PartitionedStackFn(torch.autograd.Function):
         path_e = ops.choose_path(x.dtype, cfg.act_edge, cfg.L_edge)
         path_n = ops.choose_path(x.dtype, cfg.act_node, cfg.L_node)
         scale = plan.inv_deg[:n_own].contiguous() if cfg.mean else None
+        paths_bwd = (ops.choose_path(x.dtype, cfg.act_edge, cfg.L_edge, backward=True),
+                     ops.choose_path(x.dtype, cfg.act_node, cfg.L_node, backward=True))
+        keep_h0 = ops.keeps_h0(path_e, path_n, *paths_bwd)
         saved = []
         for k in range(K):
             w_edge, w_node, w_proj, b_proj = flat[4 * k: 4 * k + 4]
@@ -137,16 +140,19 @@ class PartitionedStackFn(torch.autograd.Function):
             pn = ops.PreparedBlock(w_node.detach(), cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
             x_ext = torch.cat([x, ex.forward(x)], dim=0)
             P = torch.addmm(b_proj.detach(), x_ext, w_proj.detach().t())
+            h0e = torch.empty_like(e) if keep_h0 else None
+            h0n = torch.empty_like(x) if keep_h0 else None
             e_new, agg = ops.block_fwd(pe, e, e, P, plan.src, plan.dst, 0, D, rowptr=plan.rowptr, want_agg=True,
-                                       kind="edge_fwd")
+                                       kind="edge_fwd", h0_out=h0e)
             agg = agg[:n_own]
-            x_new, _ = ops.block_fwd(pn, agg, x, P, None, None, 2 * D, 0, main_scale=scale, kind="node_fwd")
-            saved += [x_ext, e, agg, P]     # x_ext and P are kept so the backward needs no second halo exchange
+            x_new, _ = ops.block_fwd(pn, agg, x, P, None, None, 2 * D, 0, main_scale=scale, kind="node_fwd",
+                                     h0_out=h0n)
+            # x_ext and (h_0 of both blocks | P) are kept so the backward needs no second halo exchange
+            saved += [x_ext, e, agg, h0e, h0n] if keep_h0 else [x_ext, e, agg, P, P]
             x, e = x_new, e_new
         ctx.cfg, ctx.part, ctx.K = cfg, part, K
         ctx.set_materialize_grads(False)
-        ctx.paths = (ops.choose_path(x.dtype, cfg.act_edge, cfg.L_edge, backward=True),
-                     ops.choose_path(x.dtype, cfg.act_node, cfg.L_node, backward=True))
+        ctx.paths, ctx.keep_h0 = paths_bwd, keep_h0
         ctx.save_for_backward(*saved, *flat)
         return x, e
 
@@ -156,23 +162,25 @@ class PartitionedStackFn(torch.autograd.Function):
         plan, ex, n_own = part.plan, part.exchanger, part.n_own
         path_e, path_n = ctx.paths
         saved = ctx.saved_tensors
-        acts, flat = saved[: 4 * K], saved[4 * K:]
+        acts, flat = saved[: 5 * K], saved[5 * K:]
         dt = acts[0].dtype
         G_x = torch.zeros_like(acts[0][:n_own]) if G_x is None else G_x.contiguous().to(dt)
         G_e = torch.zeros_like(acts[1]) if G_e is None else G_e.contiguous().to(dt).clone()
         scale = plan.inv_deg[:n_own].contiguous() if cfg.mean else None
         grads = [None] * (4 * K)
         for k in reversed(range(K)):
-            x_ext, e, agg, P = acts[4 * k: 4 * k + 4]
+            x_ext, e, agg, a1, a2 = acts[5 * k: 5 * k + 5]
+            P, h0e, h0n = (None, a1, a2) if ctx.keep_h0 else (a1, None, None)
             x = x_ext[:n_own]
             w_edge, w_node, w_proj, b_proj = flat[4 * k: 4 * k + 4]
             pe = ops.PreparedBlock(w_edge, cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
             pn = ops.PreparedBlock(w_node, cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
-            g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale, kind="node_bwd")
+            g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale, kind="node_bwd",
+                                               h0=h0n, n_nodes=plan.N)
             agg_eff = agg if scale is None else agg * scale[:, None]
             g_wn[: D * D] = (g_h0n.t() @ agg_eff.to(dt)).float().reshape(-1)
             G_e, g_h0e, g_we = ops.block_bwd(pe, e, P, plan.src, plan.dst, 0, D, G_e, g_agg=g_agg, has_resid_grad=True,
-                                             g_main_out=G_e, kind="edge_bwd")
+                                             g_main_out=G_e, kind="edge_bwd", h0=h0e, n_nodes=plan.N)
             g_we[: D * D] = (g_h0e.t() @ e).float().reshape(-1)
             g_psd = torch.empty((plan.N, 2 * D), dtype=dt, device=e.device)   # [g_P_s | g_P_d] over local rows
             ops.segment_reduce(g_h0e, plan.sptr, plan.sperm, plan.N, out=g_psd[:, :D])

@@ -73,21 +73,28 @@ class MGNStackFn(torch.autograd.Function):
         path_e = ops.choose_path(x.dtype, cfg.act_edge, cfg.L_edge)
         path_n = ops.choose_path(x.dtype, cfg.act_node, cfg.L_node)
         scale = plan.inv_deg if cfg.mean else None
+        paths_bwd = (ops.choose_path(x.dtype, cfg.act_edge, cfg.L_edge, backward=True),
+                     ops.choose_path(x.dtype, cfg.act_node, cfg.L_node, backward=True))
+        keep_h0 = ops.keeps_h0(path_e, path_n, *paths_bwd)
         saved = []
         for k in range(K):
             w_edge, w_node, w_proj, b_proj = flat[4 * k: 4 * k + 4]
             pe = ops.PreparedBlock(w_edge.detach(), cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
             pn = ops.PreparedBlock(w_node.detach(), cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
             P = torch.addmm(b_proj.detach(), x, w_proj.detach().t())
+            h0e = torch.empty_like(e) if keep_h0 else None
+            h0n = torch.empty_like(x) if keep_h0 else None
             e_new, agg = ops.block_fwd(pe, e, e, P, plan.src, plan.dst, 0, D, rowptr=plan.rowptr, want_agg=True,
-                                       kind="edge_fwd")
-            x_new, _ = ops.block_fwd(pn, agg, x, P, None, None, 2 * D, 0, main_scale=scale, kind="node_fwd")
-            saved += [x, e, agg, P]
+                                       kind="edge_fwd", h0_out=h0e)
+            x_new, _ = ops.block_fwd(pn, agg, x, P, None, None, 2 * D, 0, main_scale=scale, kind="node_fwd",
+                                     h0_out=h0n)
+            # tcgen05 path: the first hidden activation of both blocks is kept (the backward then skips one gather,
+            # one GEMM and one epilogue per tile and never reads P); CUDA-core path: P is kept and layer 0 recomputed
+            saved += [x, e, agg, h0e, h0n] if keep_h0 else [x, e, agg, P, P]
             x, e = x_new, e_new
         ctx.cfg, ctx.plan, ctx.K = cfg, plan, K
         ctx.set_materialize_grads(False)
-        ctx.paths = (ops.choose_path(x.dtype, cfg.act_edge, cfg.L_edge, backward=True),
-                     ops.choose_path(x.dtype, cfg.act_node, cfg.L_node, backward=True))
+        ctx.paths, ctx.keep_h0 = paths_bwd, keep_h0
         ctx.save_for_backward(*saved, *flat)
         return x, e
 
@@ -96,7 +103,7 @@ class MGNStackFn(torch.autograd.Function):
         cfg, plan, K = ctx.cfg, ctx.plan, ctx.K
         path_e, path_n = ctx.paths
         saved = ctx.saved_tensors
-        acts, flat = saved[: 4 * K], saved[4 * K:]
+        acts, flat = saved[: 5 * K], saved[5 * K:]
         dt = acts[0].dtype
         G_x = torch.zeros_like(acts[0]) if G_x is None else G_x.contiguous().to(dt)
         # G_e is updated in place layer by layer; the edge output is usually unused (no gradient materialised)
@@ -104,18 +111,20 @@ class MGNStackFn(torch.autograd.Function):
         scale = plan.inv_deg if cfg.mean else None
         grads: List[Optional[torch.Tensor]] = [None] * (4 * K)
         for k in reversed(range(K)):
-            x, e, agg, P = acts[4 * k: 4 * k + 4]     # P kept from the forward (N x 384 rows: 1/6 of the edge rows)
+            x, e, agg, a1, a2 = acts[5 * k: 5 * k + 5]
+            P, h0e, h0n = (None, a1, a2) if ctx.keep_h0 else (a1, None, None)
             w_edge, w_node, w_proj, b_proj = flat[4 * k: 4 * k + 4]
             pe = ops.PreparedBlock(w_edge, cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
             pn = ops.PreparedBlock(w_node, cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
             # node block: g_agg, gradient of the node pre-activation, MLP weight grads
             g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale,
-                                               kind="node_bwd")
+                                               kind="node_bwd", h0=h0n, n_nodes=plan.N)
             agg_eff = agg if scale is None else agg * scale[:, None]
             g_wn[: D * D] = (g_h0n.t() @ agg_eff.to(dt)).float().reshape(-1)
             # edge block: total gradient of e' = G_e + g_agg[receiver]
             G_e, g_h0e, g_we = ops.block_bwd(pe, e, P, plan.src, plan.dst, 0, D, G_e, g_agg=g_agg,
-                                             has_resid_grad=True, g_main_out=G_e, kind="edge_bwd")
+                                             has_resid_grad=True, g_main_out=G_e, kind="edge_bwd", h0=h0e,
+                                             n_nodes=plan.N)
             g_we[: D * D] = (g_h0e.t() @ e).float().reshape(-1)
             # gradients of the gathered projections: segmented sums by sender and by receiver
             # (both land in one [N, 2D] matrix, so the products with W_s | W_d are single K = 2D GEMMs)

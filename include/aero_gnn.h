@@ -173,6 +173,11 @@ typedef struct aero_block_desc {
   float* g_w;         /* packed like `w`; W_main slot is left untouched (caller: g_h0^T@main)  */
   void* workspace;
   size_t workspace_bytes;
+  /* optional [rows,128] rows of the first hidden activation h_0 = act(main W_main^T + gathered P), latent dtype.
+   * fwd: when non-NULL the kernel also stores h_0 there.  bwd: when non-NULL the kernel reads h_0 from there instead
+   * of recomputing it (main, P and idx0 are then not read and P may be NULL; the trade is +256 B/row kept from
+   * the forward for one GEMM, one gather and one epilogue less per backward tile).  AERO_PATH_UMMA only. */
+  void* h0;
 } aero_block_desc;
 
 size_t aero_block_prepared_bytes(int L, int path);

@@ -167,3 +167,37 @@ def test_umma_backward_is_deterministic():
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     for k in a[2]:
         assert torch.equal(a[2][k], b[2][k]), k
+
+
+def test_kept_h0_equals_recompute_bit_for_bit(monkeypatch):
+    """The backward that reads the h_0 rows kept by the forward gives the same bits as the one that recomputes layer 0
+    (aero_block_desc.h0; AERO_KEEP_H0=0 selects the recompute)."""
+    import aero_gnn_b200.models as M
+    from aero_gnn_b200 import ops
+    from aero_gnn_b200.meshes import wing_surface_mesh
+    from aero_gnn_b200.models._common import run_layers
+    dev = torch.device("cuda", 0)
+    mesh = wing_surface_mesh(37, 23)
+    torch.manual_seed(9)
+    net = M.MeshGraphNet(6, 4, 5, processor_size=2, num_hidden_layers_node_processor=2,
+                         num_hidden_layers_edge_processor=2, aggregation="mean", do_concat_trick=True
+                         ).to(dev).to(torch.bfloat16)
+    plan = ops.PLAN_CACHE.get(mesh.edge_index.to(dev), mesh.num_nodes)
+    g = torch.Generator().manual_seed(2)
+    x0 = torch.randn(mesh.num_nodes, 128, generator=g).to(dev, torch.bfloat16).requires_grad_(True)
+    e0 = torch.randn(mesh.num_edges, 128, generator=g).to(dev, torch.bfloat16).requires_grad_(True)
+    gx = torch.randn(mesh.num_nodes, 128, generator=g).to(dev, torch.bfloat16)
+
+    def run(keep):
+        monkeypatch.setenv("AERO_KEEP_H0", "1" if keep else "0")
+        for p in net.layers.parameters():
+            p.grad = None
+        x0.grad = e0.grad = None
+        x, e = run_layers(net.layers, plan, x0, e0)
+        torch.autograd.backward([x], [gx])
+        return [x.detach().clone(), x0.grad.clone(), e0.grad.clone()] + [p.grad.clone() for p in net.layers.parameters()]
+
+    a, b = run(True), run(False)
+    assert ops.keeps_h0(1, 1, 1, 1) is False       # env still "0" here
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
