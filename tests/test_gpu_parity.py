@@ -400,3 +400,28 @@ def test_mlp_fused_tail_bf16_and_unfusable_shapes():
     assert not MLP(128, 128, 5, num_hidden_layers=2, use_layer_norm=False).to(dev)._fusable(torch.randn(4, 128, device=dev))
     assert not MLP(6, 64, 64, num_hidden_layers=2).to(dev)._fusable(torch.randn(4, 6, device=dev))
     assert not MLP(6, 128, 128, num_hidden_layers=0).to(dev)._fusable(torch.randn(4, 6, device=dev))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_segment_reduce_into_column_blocks(dtype):
+    """aero_segment_reduce_ld: two reductions fill the column blocks of one [n, 2w] matrix and equal the plain calls;
+    malformed output views are rejected."""
+    from aero_gnn_b200 import ops
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(7)
+    n, rows, w = 301, 4000, 128
+    src = torch.randn(rows, w, generator=g).to(dev, dtype)
+    seg = torch.sort(torch.randint(0, n, (rows,), generator=g)).values
+    ptr = torch.zeros(n + 1, dtype=torch.int32)
+    ptr[1:] = torch.cumsum(torch.bincount(seg, minlength=n), 0).to(torch.int32)
+    ptr = ptr.to(dev)
+    lst = torch.randperm(rows, generator=g).to(torch.int32).to(dev)
+    both = torch.full((n, 2 * w), 7.0, dtype=dtype, device=dev)
+    ops.segment_reduce(src, ptr, lst, n, out=both[:, :w])
+    ops.segment_reduce(src, ptr, None, n, out=both[:, w:])
+    assert torch.equal(both[:, :w], ops.segment_reduce(src, ptr, lst, n))
+    assert torch.equal(both[:, w:], ops.segment_reduce(src, ptr, None, n))
+    with pytest.raises(RuntimeError):
+        ops.segment_reduce(src, ptr, None, n, out=both[:, ::2])                  # non-unit column stride
+    with pytest.raises(RuntimeError):
+        ops.segment_reduce(src, ptr, None, n, out=torch.empty(n + 1, w, dtype=dtype, device=dev))
