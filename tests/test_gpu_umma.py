@@ -201,3 +201,29 @@ def test_kept_h0_equals_recompute_bit_for_bit(monkeypatch):
     assert ops.keeps_h0(1, 1, 1, 1) is False       # env still "0" here
     for u, v in zip(a, b):
         assert torch.equal(u, v)
+
+
+def test_tmem_layout_probes():
+    """Hardware facts the next kernel design relies on (aero_umma_probe): an M = 64 accumulator
+    occupies lanes 32*(r/16) + r%16 (+16 with lane offset 16, so two of them share one column range), and a GEMM whose
+    A operand was written to tensor memory with tcgen05.st reproduces a * b^T."""
+    from aero_gnn_b200 import lib
+    L = lib.load()
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(128, 128, generator=g).to(dev, torch.bfloat16)
+    b = torch.randn(128, 128, generator=g).to(dev, torch.bfloat16)
+    ref = a.float() @ b.float().t()
+    st = torch.cuda.current_stream().cuda_stream
+    for mode, off in ((0, 0), (1, 16)):
+        c = torch.full((128, 128), float("nan"), device=dev)
+        assert L.aero_umma_probe(a.data_ptr(), b.data_ptr(), c.data_ptr(), mode, st) == 0
+        torch.cuda.synchronize()
+        want = torch.zeros(128, 128, device=dev)
+        for r in range(64):
+            want[32 * (r // 16) + r % 16 + off] = ref[r]
+        assert float((c - want).abs().max()) < 1e-3 * float(ref.abs().max())
+    c = torch.empty(128, 128, device=dev)
+    assert L.aero_umma_probe(a.data_ptr(), b.data_ptr(), c.data_ptr(), 2, st) == 0
+    torch.cuda.synchronize()
+    assert float((c - ref).abs().max()) < 1e-3 * float(ref.abs().max())
