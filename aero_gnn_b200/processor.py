@@ -51,6 +51,8 @@ def pack_block(w_main, hidden: Sequence, w_out, b_out, gamma, beta) -> torch.Ten
     parts = [w_main.reshape(-1)] + [w.reshape(-1) for (w, _) in hidden] + [w_out.reshape(-1)]
     parts += [b.reshape(-1) for (_, b) in hidden] + [b_out.reshape(-1), gamma.reshape(-1), beta.reshape(-1)]
     parts.append(torch.zeros_like(b_out.reshape(-1)))   # gradient-only slot (first Linear's bias lives in b_proj)
+    if all(p.dtype == parts[0].dtype for p in parts):
+        return torch.cat(parts).float()                 # one widening cast (exact) instead of one per parameter
     return torch.cat([p.float() for p in parts])
 
 
