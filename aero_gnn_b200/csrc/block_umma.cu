@@ -4,7 +4,8 @@
 // One persistent CTA per SM, 512 threads = two independent 256-thread tile groups.  A group owns one 128-row tile:
 //   * all (L+2) weight matrices of the block stay in shared memory for the whole kernel as bf16 SWIZZLE_128B row
 //     tiles (umma.cuh), loaded once per CTA;
-//   * the group stages its rows into its activation tile; one elected thread issues the 8 tcgen05.mma (K = 16 each)
+//   * the group stages its rows into its activation tile; the elected lane of the group's first warp (warp-uniform
+//     branch, descriptors in uniform registers) issues the 8 tcgen05.mma (K = 16 each)
 //     of a 128x128x128 GEMM into the group's 128 TMEM columns and commits to an mbarrier;
 //   * epilogue: thread = (row, 64-column half) -- warp w reads TMEM lanes 32*(w%4).., columns 64*(w/4).. with
 //     tcgen05.ld, adds the gathered pre-projections (layer 0) or the bias, applies the activation, packs to bf16

@@ -2,6 +2,7 @@
 //
 // One persistent CTA (512 threads, 16 warps) per SM owns one 128-row tile at a time and runs, per tile,
 //   forward recompute : (L+2) GEMMs   h_m = act(h_{m-1} W_m^T + ..),  y = h_L W_out^T + b
+//                       (L+1 when the forward kept h_0: aero_block_desc.h0 -- no gather, no first GEMM/epilogue)
 //   LayerNorm backward (thread = (row, 32-column chunk), row statistics exchanged through shared memory): dL/dy
 //   for m = L+1 .. 1  : dW_m += G_m^T H_{m-1}   (both operands MN-major views of the same row tiles,
 //                                               fp32 accumulators stay in TMEM for the whole kernel)
@@ -16,6 +17,9 @@
 // Epilogues: warp w reads TMEM lanes 32*(w%4).., columns 32*(w/4)..; one 32-column chunk per thread.
 // Bias / LayerNorm-parameter gradients are column sums over the bf16 tiles (thread = (column, row quarter)),
 // taken while the MMAs run.  Per-CTA partial gradients are written once at the end and reduced in CTA order.
+// The MMAs of a phase are issued by the elected lane of warp 0 inside a warp-uniform branch (umma.cuh: elect_one),
+// which keeps the descriptors in uniform registers; every staging phase issues all its global loads before its
+// first shared-memory store.
 #include "umma_block.cuh"
 
 namespace aero {
