@@ -3,8 +3,9 @@
 Parameter names are the checkpoint contract: `layers.{i}.weight|bias` and `layer_norm.weight|bias`
 (SURVEY.md section 8b).  Inside a processor step the Linear/LayerNorm chain is executed by the fused
 block kernels (processor.py reads the parameters through `split_first` / `tail`); called on its own
-(encoders) everything after its first Linear runs on the same fused block kernel (processor.DenseTailFn);
-shapes the kernel does not cover (the decoder's narrow output layer) stay a dense row-wise chain of library ops.
+(encoders) everything after its first Linear runs on the same fused block kernel (processor.DenseTailFn); a
+128-wide input (the decoder) runs whole on it, a narrower last Linear zero-padded (processor.DenseMLPFn); shapes
+the kernel does not cover stay a dense row-wise chain of library ops.
 """
 from __future__ import annotations
 
@@ -41,13 +42,23 @@ class MLP(nn.Module):
             return False
         if self.training and self.dropout.p > 0:
             return False
-        return all(l.out_features == D for l in self.layers) and all(l.in_features == D for l in self.layers[1:])
+        if not all(l.out_features == D for l in self.layers[:-1]) or not all(l.in_features == D for l in self.layers[1:]):
+            return False
+        # last Linear: D wide, or narrower without LayerNorm (zero-padded to D columns; needs a D-wide input so the
+        # first Linear is the kernel's own first GEMM -- the decoder, mgn.py:130)
+        out = self.layers[-1].out_features
+        return out == D or (out < D and not self.use_layer_norm and self.layers[0].in_features == D)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self._fusable(x):
-            from ..processor import dense_tail
-            z = self.layers[0](x)                      # [rows, in] x [in, 128]: a thin library GEMM, bias included
+            from ..ops import D
+            from ..processor import dense_mlp, dense_tail
             hidden, w_out, b_out, gamma, beta = self.tail()
+            if self.layers[0].in_features == D:
+                out = dense_mlp(len(hidden), self.activation_name, self.use_layer_norm, x, self.layers[0].weight,
+                                self.layers[0].bias, hidden, w_out, b_out, gamma, beta)
+                return out if w_out.size(0) == D else out[:, : w_out.size(0)]
+            z = self.layers[0](x)                      # [rows, in] x [in, 128]: a thin library GEMM, bias included
             return dense_tail(len(hidden), self.activation_name, self.use_layer_norm, z, hidden, w_out, b_out,
                               gamma, beta)
         last = len(self.layers) - 1

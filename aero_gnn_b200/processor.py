@@ -302,3 +302,43 @@ def dense_tail(L: int, act: str, use_ln: bool, z: torch.Tensor, hidden: Sequence
         eye = _EYE[key] = torch.eye(D, dtype=torch.float32, device=z.device)
     w = pack_block(eye, hidden, w_out, b_out, gamma, beta)
     return DenseTailFn.apply(L, act, use_ln, z, w)
+
+
+class DenseMLPFn(torch.autograd.Function):
+    """A whole MLP whose input is D wide (the decoder, mgn.py:130): out = [LN](W_out act(.. act(W_0 x + b_0) ..) + b_out).
+    W_0 is the block's real first GEMM, b_0 its single pre-projection row; a narrower last Linear is zero-padded to
+    D output columns by the caller (the padded columns are zeros and carry zero gradient)."""
+
+    @staticmethod
+    def forward(ctx, L: int, act: str, use_ln: bool, x: torch.Tensor, w: torch.Tensor, b0: torch.Tensor):
+        ops._require_cuda(x, w, b0)
+        x = x.contiguous()
+        P = b0.detach().to(x.dtype).reshape(1, D).contiguous()
+        idx0 = _zero_idx(x.size(0), x.device)
+        prep = ops.PreparedBlock(w.detach(), L, ops.choose_path(x.dtype, act, L), act, use_ln)
+        out, _ = ops.block_fwd(prep, x, None, P, idx0, None, 0, 0, kind="dense_fwd")
+        ctx.meta = (L, act, use_ln, ops.choose_path(x.dtype, act, L, backward=True), b0.dtype)
+        ctx.save_for_backward(x, w, P, idx0)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L, act, use_ln, path, b0_dtype = ctx.meta
+        x, w, P, idx0 = ctx.saved_tensors
+        prep = ops.PreparedBlock(w, L, path, act, use_ln)
+        g_x, g_h0, g_w = ops.block_bwd(prep, x, P, idx0, None, 0, 0, g.contiguous().to(x.dtype), kind="dense_bwd")
+        g_w[: D * D] = (g_h0.t() @ x).float().reshape(-1)          # dW_0 = g_h0^T x (library GEMM, like the processor)
+        return None, None, None, g_x, g_w, g_w[-D:].to(b0_dtype)   # last slot: column sums of g_h0 = d b_0
+
+
+def dense_mlp(L: int, act: str, use_ln: bool, x: torch.Tensor, w0, b0, hidden: Sequence, w_out, b_out, gamma, beta):
+    """x [rows, D] through a full MLP on the fused block kernel; returns [rows, D] (columns >= w_out.size(0) are 0)."""
+    out_dim = w_out.size(0)
+    if out_dim < D:
+        pad = D - out_dim
+        w_out = torch.cat([w_out, w_out.new_zeros((pad, D))], dim=0)
+        b_out = torch.cat([b_out, b_out.new_zeros(pad)])
+        gamma = torch.cat([gamma, gamma.new_ones(pad)])
+        beta = torch.cat([beta, beta.new_zeros(pad)])
+    w = pack_block(w0, hidden, w_out, b_out, gamma, beta)
+    return DenseMLPFn.apply(L, act, use_ln, x, w, b0)

@@ -397,7 +397,8 @@ def test_mlp_fused_tail_bf16_and_unfusable_shapes():
     ref = torch.nn.functional.layer_norm(h, (128,), mlp.layer_norm.weight.float(), mlp.layer_norm.bias.float())
     assert rrmse(out.float(), ref) < 1e-2, rrmse(out.float(), ref)     # bf16 tolerance of the north star
     # shapes the kernel does not cover stay on the library chain
-    assert not MLP(128, 128, 5, num_hidden_layers=2, use_layer_norm=False).to(dev)._fusable(torch.randn(4, 128, device=dev))
+    assert not MLP(128, 128, 5, num_hidden_layers=2, use_layer_norm=True).to(dev)._fusable(torch.randn(4, 128, device=dev))
+    assert not MLP(6, 128, 5, num_hidden_layers=2, use_layer_norm=False).to(dev)._fusable(torch.randn(4, 6, device=dev))
     assert not MLP(6, 64, 64, num_hidden_layers=2).to(dev)._fusable(torch.randn(4, 6, device=dev))
     assert not MLP(6, 128, 128, num_hidden_layers=0).to(dev)._fusable(torch.randn(4, 6, device=dev))
 
@@ -425,3 +426,34 @@ def test_segment_reduce_into_column_blocks(dtype):
         ops.segment_reduce(src, ptr, None, n, out=both[:, ::2])                  # non-unit column stride
     with pytest.raises(RuntimeError):
         ops.segment_reduce(src, ptr, None, n, out=torch.empty(n + 1, w, dtype=dtype, device=dev))
+
+
+@pytest.mark.parametrize("rows,out_dim,nh,ln", [(1, 5, 2, False), (777, 4, 1, False), (3000, 128, 2, True)])
+def test_mlp_fused_decoder_fp32_vs_chain(rows, out_dim, nh, ln):
+    """A 128-wide input (the decoder, mgn.py:130) runs whole on the block kernel; a narrow last Linear is zero-padded."""
+    from aero_gnn_b200.models.mlp import MLP
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(rows + out_dim)
+    mlp = MLP(128, 128, out_dim, num_hidden_layers=nh, use_layer_norm=ln).to(dev)
+    x = torch.randn(rows, 128, device=dev, requires_grad=True)
+    g = torch.randn(rows, out_dim, device=dev)
+    assert mlp._fusable(x)
+    out = mlp(x)
+    assert out.shape == (rows, out_dim)
+    out.backward(g)
+    got = [x.grad.clone()] + [p.grad.clone() for p in mlp.parameters()]
+    x.grad = None
+    mlp.zero_grad(set_to_none=True)
+    h = x.double()
+    lay = list(mlp.layers)
+    for i, lin in enumerate(lay):
+        h = torch.nn.functional.linear(h, lin.weight.double(), lin.bias.double())
+        if i < len(lay) - 1:
+            h = torch.relu(h)
+    if ln:
+        h = torch.nn.functional.layer_norm(h, (out_dim,), mlp.layer_norm.weight.double(), mlp.layer_norm.bias.double())
+    h.backward(g.double())
+    want = [x.grad] + [p.grad for p in mlp.parameters()]
+    assert rel_err(out, h) < 1e-5, rel_err(out, h)
+    for a, b in zip(got, want):
+        assert rel_err(a, b) < 1e-4, rel_err(a, b)
