@@ -43,11 +43,15 @@ class FourierMeshGraphNet(nn.Module):
     def fourier_embedding(self, pos: torch.Tensor) -> torch.Tensor:
         """[cos(2^i pi x) for all i | sin(2^i pi x) for all i] per spatial dim, flattened per node
         (layout of fouriermgn.py:143-149: [N, dim, 2*F] -> [N, dim*2*F])."""
-        xs = pos[:, : self.fourier_features_dim]
+        # phases and sin/cos are evaluated in (at least) fp32 and rounded once: with bf16 latents the reference's
+        # bf16-mode phase 2^i*pi*x (up to ~25 rad) would carry ~0.05 rad of rounding error
+        wide = torch.float32 if pos.dtype in (torch.bfloat16, torch.float16) else pos.dtype
+        xs = pos[:, : self.fourier_features_dim].to(wide)
         k = torch.arange(self.fourier_freq_start, self.fourier_freq_start + self.fourier_freq_length,
-                         device=pos.device, dtype=pos.dtype)
+                         device=pos.device, dtype=wide)
         phase = ((2.0 ** k) * math.pi).view(1, 1, -1) * xs.unsqueeze(-1)
-        return torch.cat([torch.cos(phase), torch.sin(phase)], dim=-1).reshape(pos.shape[0], -1)
+        emb = torch.cat([torch.cos(phase), torch.sin(phase)], dim=-1).reshape(pos.shape[0], -1)
+        return emb.to(pos.dtype)
 
     def forward(self, node_attr, edge_attr, edge_index):
         ops._require_cuda(node_attr, edge_attr, edge_index)

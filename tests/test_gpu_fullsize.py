@@ -184,7 +184,13 @@ def test_c3_c4_models_at_100k_nodes_bf16_vs_fp32():
         # MGN-style models meet the 1e-2 bound of the north star.  The 4-level BSMS U-Net runs 15 processor steps plus
         # 3 mean-pool and 3 unpool+skip stages, every one of which rounds the bf16 residual streams once more; its
         # measured error is 2.4e-2 and is bounded at 3e-2 here.
-        # poolMGN / FourierMGN: the prologues (global encoder + mean pool over 100k nodes, Fourier features up to
-        # 2^3*pi*x) run as plain torch bf16 ops like the reference's bf16 mode and dominate their error.
-        bound = {"bsms": 3e-2, "poolmgn": 6e-2, "fourier": 6e-2}[name]
+        # poolMGN / FourierMGN: the ABSOLUTE error is the same as plain MGN's on this mesh (per-feature RMSE ~1e-3,
+        # scripts/diag_bf16_models.py: MGN 0.0091, rel-L2 0.0073); their random-initialised heads leave some output
+        # channels with a mean magnitude of 0.01-0.03, which inflates the per-feature relative metric (0.046 / 0.032)
+        # while the relative L2 error over all channels stays at 1.0e-2 / 1.1e-2.
+        bound = {"bsms": 3e-2, "poolmgn": 6e-2, "fourier": 4.5e-2}[name]
         assert err < bound, (name, err)
+        e = (out.float() - ref).detach()
+        # absolute per-channel RMSE (BSMS: ~2x MGN's, its pooled streams are rounded more often), relative L2
+        assert float(e.pow(2).mean(0).sqrt().max()) < (4e-3 if name == "bsms" else 2.5e-3), name
+        assert float(e.norm() / ref.norm()) < (2.5e-2 if name == "bsms" else 1.3e-2), name
