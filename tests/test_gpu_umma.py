@@ -169,7 +169,8 @@ def test_umma_backward_is_deterministic():
         assert torch.equal(a[2][k], b[2][k]), k
 
 
-def test_kept_h0_equals_recompute_bit_for_bit(monkeypatch):
+@pytest.mark.parametrize("nh,agg", [(2, "mean"), (1, "add")])
+def test_kept_h0_equals_recompute_bit_for_bit(monkeypatch, nh, agg):
     """The backward that reads the h_0 rows kept by the forward gives the same bits as the one that recomputes layer 0
     (aero_block_desc.h0; AERO_KEEP_H0=0 selects the recompute)."""
     import aero_gnn_b200.models as M
@@ -179,8 +180,8 @@ def test_kept_h0_equals_recompute_bit_for_bit(monkeypatch):
     dev = torch.device("cuda", 0)
     mesh = wing_surface_mesh(37, 23)
     torch.manual_seed(9)
-    net = M.MeshGraphNet(6, 4, 5, processor_size=2, num_hidden_layers_node_processor=2,
-                         num_hidden_layers_edge_processor=2, aggregation="mean", do_concat_trick=True
+    net = M.MeshGraphNet(6, 4, 5, processor_size=2, num_hidden_layers_node_processor=nh,
+                         num_hidden_layers_edge_processor=nh, aggregation=agg, do_concat_trick=(nh == 2)
                          ).to(dev).to(torch.bfloat16)
     plan = ops.PLAN_CACHE.get(mesh.edge_index.to(dev), mesh.num_nodes)
     g = torch.Generator().manual_seed(2)
