@@ -30,7 +30,10 @@ constexpr int BWD_THREADS = 512;
 // phase into g_phase[]; read back with aero_debug_phase_read().  Compiled out of the production library.
 #ifdef AERO_PHASE_TIMING
 __device__ long long g_phase[32];
-#define PHASE_INIT() long long _pt = clock64(); const bool _obs = (blockIdx.x == 0 && threadIdx.x == 64)
+#ifndef AERO_PHASE_TID
+#define AERO_PHASE_TID 64   // observer thread; 0 = the MMA-issuing lane (then phases 15..18 time acquire / issue)
+#endif
+#define PHASE_INIT() long long _pt = clock64(); const bool _obs = (blockIdx.x == 0 && threadIdx.x == AERO_PHASE_TID)
 #define PHASE(k) do { if (_obs) { long long _n = clock64(); g_phase[k] += _n - _pt; _pt = _n; } } while (0)
 #else
 #define PHASE_INIT() do { } while (0)
@@ -251,7 +254,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
     const int m_first = have_h0 ? 1 : 0;
     for (int m = m_first; m <= L + 1; ++m) {
       if (w0) {
+        PHASE(19);  // (lane 0) arrival at the issue point
         uint32_t wa = acquire(m);
+        PHASE(15);  // (lane 0) recompute: wait for the weight slot
         fence_after_sync();
         uint32_t a_addr = (m == 0) ? x_s : x_s + (uint32_t)h_tile(m - 1) * TILE_BYTES;
         if (elect_one()) {
@@ -260,6 +265,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
         }
         __syncwarp();
         if (m + 1 <= L + 1) prefetch(m + 1);   // other slot: last read by GEMM m-1, already complete
+        PHASE(16);  // (lane 0) recompute: MMA issue + next weight prefetch
       }
       if (m == 0) {
         // under the first MMA: the coalesced gather P_s[src] + P_d[dst] into the (still free) tile that will hold
@@ -370,7 +376,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
     uint32_t gc_s = g_s;
     for (int m = L + 1; m >= 0; --m) {
       if (w0) {
+        PHASE(19);
         uint32_t wa = acquire(m);
+        PHASE(17);  // (lane 0) backward: wait for the weight slot
         fence_after_sync();
         if (elect_one()) {
           if (m >= 1) {
@@ -382,6 +390,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) umma_block_bwd_kernel(UmmaArgs
         }
         __syncwarp();
         if (m >= 1) prefetch(m - 1);
+        PHASE(18);  // (lane 0) backward: MMA issue + next weight prefetch
       }
       PHASE(14);  // bwd: (thread 0: MMA issue)
       if (m >= 1) db[m - 1] += tile_col_sums_512(Gc, wid, lane);   // bias gradient of Linear m

@@ -114,9 +114,64 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __nv_bfloat16*
   if (tid < 32) tmem_dealloc<256>(tacc);
 }
 
+// MMA throughput per operand orientation: `reps` back-to-back 128x128x128 GEMMs (8 MMAs each) between two clock
+// reads taken by the issuing thread around issue .. commit-wait; out[0] = cycles, out[1] = MMAs issued.
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(const __nv_bfloat16* __restrict__ Ag,
+                                                           const __nv_bfloat16* __restrict__ Bg, long long* __restrict__ out,
+                                                           int a_mn, int b_mn, int reps) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* At = smem;
+  uint8_t* Bt = smem + TILE_BYTES;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(Bt + TILE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  const int tid = threadIdx.x;
+  stage_rows<false, 128>(At, Ag, nullptr, 0, 128, tid);
+  stage_rows<false, 128>(Bt, Bg, nullptr, 0, 128, tid);
+  if (tid == 0) {
+    mbar_init(smem_u32(mbar), 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) tmem_alloc<128>(tmem_slot);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tacc = *tmem_slot;
+  if (tid < 32) {
+    long long t0 = clock64();
+    if (elect_one()) {
+      for (int r = 0; r < reps; ++r) issue_gemm(tacc, smem_u32(At), a_mn != 0, smem_u32(Bt), b_mn != 0, r > 0);
+      mma_commit(smem_u32(mbar));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(mbar), 0);
+    long long t1 = clock64();
+    if (tid == 0) {
+      out[0] = t1 - t0;
+      out[1] = 8LL * reps;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc<128>(tacc);
+}
+
 }  // namespace aero
 
 using namespace aero;
+
+extern "C" int aero_umma_rate_probe(const void* a_bf16, const void* b_bf16, long long* out2, int a_mn, int b_mn, int reps,
+                                    void* stream) {
+  AERO_CHECK_ARG(a_bf16 && b_bf16 && out2 && reps > 0, "aero_umma_rate_probe: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t smem = 1024 + 2 * umma::TILE_BYTES + 64;
+  AERO_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_rate_kernel<<<1, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(a_bf16),
+                                         reinterpret_cast<const __nv_bfloat16*>(b_bf16), out2, a_mn, b_mn, reps);
+  AERO_LAUNCH_CHECK();
+  return AERO_OK;
+}
 
 extern "C" int aero_umma_probe(const void* a_bf16, const void* b_bf16, float* c, int mode, void* stream) {
   AERO_CHECK_ARG(a_bf16 && b_bf16 && c && mode >= 0 && mode <= 2, "aero_umma_probe: bad arguments");

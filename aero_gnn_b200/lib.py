@@ -42,6 +42,7 @@ SIGNATURES = {
     "aero_has_umma_bwd": (C.c_int, []),
     "aero_umma_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "aero_umma_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "aero_umma_rate_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "aero_last_launch_count": (C.c_int, []),
     "aero_graph_plan_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "aero_graph_plan_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 7 + [C.c_void_p, C.c_size_t, C.c_void_p]),

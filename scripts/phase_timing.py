@@ -17,13 +17,13 @@ e0 = torch.randn(mesh.num_edges, 128, generator=g).to(dev, torch.bfloat16).requi
 L = lib.load()
 fn = L.aero_debug_phase_read; fn.argtypes = [C.c_void_p, C.c_int]; fn.restype = C.c_int
 buf = (C.c_longlong * 32)()
-names = ["tile-top sync", "staging", "fwd issue+colsum", "fwd MMA wait", "fwd epilogues", "LN backward", "bwd issue+colsum", "bwd MMA wait", "bwd epilogues", "-", "bwd tcgen05.ld", "bwd mask+store", "bwd fences", "bwd barrier", "bwd pre-colsum", "stage main+idx", "stage g_tot"]
+names = ["tile-top sync", "staging", "fwd issue+colsum", "fwd MMA wait", "fwd epilogues", "LN backward", "bwd issue+colsum", "bwd MMA wait", "bwd epilogues", "-", "bwd tcgen05.ld", "bwd mask+store", "bwd fences", "bwd barrier", "bwd pre-colsum", "(lane0) fwd weight wait", "(lane0) fwd issue", "(lane0) bwd weight wait", "(lane0) bwd issue", "(lane0) to issue point"]
 for it in range(3):
     x, e = run_layers(net.layers, plan, x0, e0)
     fn(buf, 1)       # reset after forward
     torch.autograd.backward([x], [torch.ones_like(x)])
     fn(buf, 1)
-    v = list(buf)[:17]
+    v = list(buf)[:20]
     # the backward runs the node block kernel then the edge block kernel: both accumulate; report the sum
     tot = sum(v)
     print("iter", it, "total cycles (CTA0 observer, node+edge bwd kernels):", tot)

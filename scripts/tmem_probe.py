@@ -46,3 +46,13 @@ for mode in (0, 1, 2):
     for l0, l1, r0, r1 in runs:
         print(f"   TMEM lanes {l0:3d}..{l1:3d}  <-  rows {r0:2d}..{r1:2d} of the 64-row product")
     print("   worst match error:", max((e for _, _, e in lanes), default=float('nan')))
+
+# ---- MMA rate per operand orientation ----
+out2 = torch.zeros(2, dtype=torch.int64, device=dev)
+for a_mn, b_mn, what in ((0, 0, "A K-major, B K-major (forward)"), (0, 1, "A K-major, B MN-major (data gradient)"),
+                         (1, 1, "A MN-major, B MN-major (weight gradient)")):
+    for reps in (1, 4, 32):
+        L.aero_umma_rate_probe(a.data_ptr(), b.data_ptr(), out2.data_ptr(), a_mn, b_mn, reps, st)
+        torch.cuda.synchronize()
+        cyc, n = int(out2[0]), int(out2[1])
+        print(f"{what}: {n:4d} MMAs (128x128x16) in {cyc:6d} cycles = {cyc / n:6.1f} cycles/MMA")
