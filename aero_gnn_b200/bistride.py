@@ -1,0 +1,318 @@
+"""BFS-bistride pooling index construction and WeightedEdgeConv on the sm_100a kernels of csrc/bistride.cu.
+
+Follows the reference's bistride_ops module, which ships only as bytecode
+(models/__pycache__/bistride_ops.cpython-311.pyc; "orig :NN" = first line of the code object) and the older
+BSMS design in models/__pycache__/bsms_mgn.cpython-311.pyc (MultiScaleGraphPreprocessor orig :18).
+
+Index work (BFS levels, even-level selection, coarse edge lists) runs once per mesh and is cached by content hash;
+it is bit-exact.  WeightedEdgeConv is one autograd node: a plain GEMM pre-projects the node rows, the fused gather
+kernels do everything per edge (length, edge-weight MLP, sigmoid, weighted sum onto receivers) without atomics.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import lib as _l
+from . import ops
+from .ops import _ptr, _stream, _workspace
+from .pooling import _hash_any
+
+WEC_HID = 64
+BFS_LEVELS_PER_CALL = 64
+
+
+# ------------------------------------------------------------------------------------------------
+# BFS levels / selection / coarse edges
+# ------------------------------------------------------------------------------------------------
+def bfs_levels(plan: ops.GraphPlan, start: int) -> torch.Tensor:
+    """int64 [N] hop count from `start` along sender->receiver edges, -1 when unreachable (bfs_distance, orig :21)."""
+    lib = _l.load()
+    dev = plan.rowptr.device
+    N = plan.N
+    if not 0 <= int(start) < N:
+        raise IndexError(f"start node {start} outside [0, {N})")
+    dist = torch.empty(N, dtype=torch.int64, device=dev)
+    status = torch.zeros(2, dtype=torch.int64, device=dev)
+    ws = _workspace(lib.aero_bfs_levels_workspace_bytes(N), dev)
+    level = 0
+    with torch.cuda.device(dev):
+        while True:
+            rc = lib.aero_bfs_levels(_ptr(plan.sptr), _ptr(plan.sperm), _ptr(plan.dst), N, plan.E, int(start), level,
+                                     BFS_LEVELS_PER_CALL, _ptr(dist), _ptr(status), _ptr(ws), ws.numel(), _stream())
+            _l.check(rc, "aero_bfs_levels")
+            ops.LaunchCounter.add()
+            level += BFS_LEVELS_PER_CALL
+            if int(status[0].item()) == 0:   # one readback per 64 levels (the reference: one .item() per edge)
+                break
+    return dist
+
+
+def seed_node(edge_index: torch.Tensor, num_nodes: int, pos: Optional[torch.Tensor], plan: ops.GraphPlan) -> int:
+    """select_bistride_nodes' seed (orig :56): the node nearest to the centroid of `pos`, else the node with the most
+    outgoing edges; first index on ties (torch.argmin / argmax)."""
+    if pos is not None:
+        center = pos.mean(dim=0)
+        return int(torch.argmin(torch.norm(pos - center, dim=1)).item())
+    deg = plan.sptr[1:] - plan.sptr[:-1]          # == bincount(edge_index[0], minlength=N)
+    return int(torch.argmax(deg).item())
+
+
+def bistride_select(dist: torch.Tensor):
+    """(selected int64 ascending, index_map int64 [N], fallback: bool) from BFS distances (orig :56 + bsms :32)."""
+    ops._require_cuda(dist)
+    lib = _l.load()
+    N = int(dist.numel())
+    dev = dist.device
+    selected = torch.empty(N, dtype=torch.int64, device=dev)
+    index_map = torch.empty(N, dtype=torch.int64, device=dev)
+    counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    ws = _workspace(lib.aero_bistride_select_workspace_bytes(N), dev)
+    with torch.cuda.device(dev):
+        rc = lib.aero_bistride_select(_ptr(dist), N, _ptr(selected), _ptr(index_map), _ptr(counts), _ptr(ws), ws.numel(),
+                                      _stream())
+    _l.check(rc, "aero_bistride_select")
+    ops.LaunchCounter.add()
+    c = counts.tolist()
+    return selected[: c[0]].clone(), index_map, bool(c[1])
+
+
+def filter_edges(edge_index: torch.Tensor, index_map: torch.Tensor):
+    """Coarse edge_index [2, Ec] int64 (both endpoints selected, renumbered, self-loops dropped, caller order) and the
+    caller edge id of every kept edge (int32 [Ec])."""
+    ops._require_cuda(edge_index, index_map)
+    lib = _l.load()
+    ei = edge_index.long().contiguous()
+    E, N = int(ei.size(1)), int(index_map.numel())
+    dev = ei.device
+    out = torch.empty((2, max(E, 1)), dtype=torch.int64, device=dev)
+    kept = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    ws = _workspace(lib.aero_filter_edges_workspace_bytes(E), dev)
+    with torch.cuda.device(dev):
+        rc = lib.aero_filter_edges(_ptr(ei), E, _ptr(index_map), N, _ptr(out), _ptr(kept), _ptr(counts), _ptr(ws),
+                                   ws.numel(), _stream())
+    _l.check(rc, "aero_filter_edges")
+    ops.LaunchCounter.add()
+    c = counts.tolist()
+    if c[1]:
+        raise IndexError(f"edge_index holds {c[1]} edges with an endpoint outside [0, {N})")
+    # `out` is [2, E] contiguous, i.e. the row stride E the kernel writes with
+    return out[:, : c[0]].contiguous(), kept[: c[0]].clone()
+
+
+def select_bistride_nodes(edge_index: torch.Tensor, num_nodes: int, pos: Optional[torch.Tensor] = None) -> torch.Tensor:
+    ops._require_cuda(edge_index, pos)
+    plan = ops.PLAN_CACHE.get(edge_index, num_nodes)
+    dist = bfs_levels(plan, seed_node(edge_index, num_nodes, pos, plan))
+    return bistride_select(dist)[0]
+
+
+@dataclass
+class BistrideLevel:
+    selected: torch.Tensor        # int64 [Nc] ascending fine ids kept at the coarser level
+    sel32: torch.Tensor           # int32 copy (row gathers)
+    index_map: torch.Tensor       # int64 [N]: coarse id or -1
+    index_map32: torch.Tensor     # int32 copy (Unpool gathers; -1 = zero row)
+    coarse_edge_index: torch.Tensor   # int64 [2, Ec]
+    kept_edges: torch.Tensor      # int32 [Ec] fine edge id of every coarse edge
+    fallback: bool
+
+
+class BistrideCache:
+    """One coarsening step per (edge_index, N, pos) content hash: epochs revisit the same meshes."""
+
+    def __init__(self, capacity: int = 64):
+        self.capacity = capacity
+        self._d: "OrderedDict[tuple, BistrideLevel]" = OrderedDict()
+
+    def get(self, edge_index: torch.Tensor, num_nodes: int, pos: Optional[torch.Tensor]) -> BistrideLevel:
+        key = (_hash_any(edge_index), _hash_any(pos), int(num_nodes), tuple(edge_index.shape), str(edge_index.device))
+        lvl = self._d.get(key)
+        if lvl is None:
+            plan = ops.PLAN_CACHE.get(edge_index, num_nodes)
+            dist = bfs_levels(plan, seed_node(edge_index, num_nodes, pos, plan))
+            selected, index_map, fb = bistride_select(dist)
+            cei, kept = filter_edges(edge_index, index_map)
+            lvl = BistrideLevel(selected, selected.to(torch.int32), index_map, index_map.to(torch.int32), cei, kept, fb)
+            self._d[key] = lvl
+            while len(self._d) > self.capacity:
+                self._d.popitem(last=False)
+        else:
+            self._d.move_to_end(key)
+        return lvl
+
+    def clear(self) -> None:
+        self._d.clear()
+
+
+BISTRIDE_CACHE = BistrideCache()
+
+
+# ------------------------------------------------------------------------------------------------
+# pool (row subset) / unpool (zero fill) with their exact adjoints
+# ------------------------------------------------------------------------------------------------
+class SelectRowsFn(torch.autograd.Function):
+    """coarse = fine[selected]  (BSMSGMP.forward pool, bsms orig :145); adjoint = Unpool."""
+
+    @staticmethod
+    def forward(ctx, fine, sel32, index_map32):
+        ctx.meta = (index_map32, fine.size(0))
+        return ops.gather_rows(fine, sel32)
+
+    @staticmethod
+    def backward(ctx, g):
+        index_map32, n = ctx.meta
+        return unpool_rows(g.contiguous(), index_map32, n), None, None
+
+
+def unpool_rows(coarse: torch.Tensor, index_map32: torch.Tensor, n_fine: int) -> torch.Tensor:
+    """fine[i] = coarse[index_map[i]] where index_map[i] >= 0, else 0 (Unpool.forward, orig :102)."""
+    if index_map32.numel() != n_fine:
+        raise RuntimeError(f"index map has {index_map32.numel()} entries for {n_fine} fine nodes")
+    return ops.gather_rows(coarse, index_map32)      # a negative index reads a zero row
+
+
+class UnpoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coarse, sel32, index_map32, n_fine: int):
+        ctx.sel32 = sel32
+        return unpool_rows(coarse.contiguous(), index_map32, n_fine)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.gather_rows(g.contiguous(), ctx.sel32), None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# WeightedEdgeConv
+# ------------------------------------------------------------------------------------------------
+def _wec_desc(plan: ops.GraphPlan, Q: torch.Tensor, out_dim: int, mean: bool, compute_w: bool, pos, w1_len, w2, b2, w):
+    d = _l.WecDesc()
+    d.dtype = ops.dtype_code(Q)
+    d.mean, d.compute_w = int(mean), int(compute_w)
+    d.pos_dim = int(pos.size(1)) if pos is not None else 0
+    d.N, d.E, d.out_dim, d.ldq = plan.N, plan.E, int(out_dim), int(Q.size(1))
+    d.Q = Q.data_ptr()
+    d.pos = pos.data_ptr() if pos is not None else None
+    d.w1_len = w1_len.data_ptr() if w1_len is not None else None
+    d.w2 = w2.data_ptr() if w2 is not None else None
+    d.b2 = b2.data_ptr() if b2 is not None else None
+    for name in ("rowptr", "src", "dst", "perm", "sptr", "sperm"):
+        setattr(d, name, getattr(plan, name).data_ptr())
+    d.w = w.data_ptr()
+    return d
+
+
+class WecFn(torch.autograd.Function):
+    """(out, w) = WeightedEdgeConv.forward (orig :173).
+
+    apply(plan, mean, out_dim, x, pos32, w_cat, b_cat, w1_len, w2, b2, edge_weights)
+      compute (edge_weights is None): w_cat = [W1_src; W1_dst; Wt] ([128+out, in]), b_cat = [0; b1; bt]
+      reuse   (edge_weights given)  : w_cat = Wt, b_cat = bt; w1_len / w2 / b2 / pos32 are None
+    """
+
+    @staticmethod
+    def forward(ctx, plan, mean, out_dim, x, pos32, w_cat, b_cat, w1_len, w2, b2, edge_weights):
+        ops._require_cuda(x, pos32, w_cat, edge_weights)
+        lib = _l.load()
+        compute = edge_weights is None
+        x = x.contiguous()
+        dt = x.dtype
+        Q = torch.addmm(b_cat.detach().to(dt), x, w_cat.detach().to(dt).t())      # plain library GEMM on N rows
+        f32 = lambda t: None if t is None else t.detach().float().contiguous()
+        w1l, w2f, b2f = f32(w1_len), f32(w2), f32(b2)
+        if compute:
+            w = torch.empty((plan.E, 1), dtype=dt, device=x.device)
+        else:
+            if edge_weights.numel() != plan.E:
+                raise RuntimeError(f"edge_weights has {edge_weights.numel()} entries for {plan.E} edges")
+            w = edge_weights.detach().to(dt).reshape(plan.E, 1).contiguous()
+        out = torch.empty((plan.N, out_dim), dtype=dt, device=x.device)
+        d = _wec_desc(plan, Q, out_dim, mean, compute, pos32, w1l, w2f, b2f, w)
+        d.out = out.data_ptr()
+        with torch.cuda.device(x.device):
+            rc = lib.aero_wec_fwd(C.byref(d), _stream())
+        _l.check(rc, "aero_wec_fwd")
+        ops.LaunchCounter.add()
+        ctx.meta = (plan, mean, out_dim, compute, pos32, w1l, w2f, b2f,
+                    None if compute else edge_weights.shape, None if compute else edge_weights.dtype)
+        ctx.save_for_backward(x, Q, w, w_cat, b_cat, w1_len, w2, b2)
+        ctx.set_materialize_grads(False)
+        if not compute:
+            ctx.mark_non_differentiable(w)   # the caller keeps using its own edge_weights tensor
+        return out, w
+
+    @staticmethod
+    def backward(ctx, g_out, g_w_ext):
+        lib = _l.load()
+        plan, mean, out_dim, compute, pos32, w1l, w2f, b2f, ew_shape, ew_dtype = ctx.meta
+        x, Q, w, w_cat, b_cat, w1_len, w2, b2 = ctx.saved_tensors
+        dt, dev = x.dtype, x.device
+        g_out = torch.zeros((plan.N, out_dim), dtype=dt, device=dev) if g_out is None else g_out.contiguous().to(dt)
+        gwx = None
+        if compute and g_w_ext is not None:
+            gwx = g_w_ext.contiguous().to(dt).reshape(-1)
+        d = _wec_desc(plan, Q, out_dim, mean, compute, pos32, w1l, w2f, b2f, w)
+        dQ = torch.empty_like(Q)
+        g_small = torch.zeros(2 * WEC_HID + 1, dtype=torch.float32, device=dev) if compute else None
+        g_w = None if compute else torch.empty((plan.E, 1), dtype=dt, device=dev)
+        d.g_out, d.dQ = g_out.data_ptr(), dQ.data_ptr()
+        d.g_w_ext = gwx.data_ptr() if gwx is not None else None
+        d.g_small = g_small.data_ptr() if compute else None
+        d.g_w = g_w.data_ptr() if g_w is not None else None
+        ws = _workspace(lib.aero_wec_workspace_bytes(C.byref(d), 1), dev)
+        d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+        with torch.cuda.device(dev):
+            rc = lib.aero_wec_bwd(C.byref(d), _stream())
+        _l.check(rc, "aero_wec_bwd")
+        ops.LaunchCounter.add()
+        g_x = dQ @ w_cat.to(dt)
+        g_wcat = (dQ.t() @ x).to(w_cat.dtype)
+        g_bcat = dQ.float().sum(dim=0).to(b_cat.dtype)
+        if compute:
+            g_w1l = g_small[:WEC_HID].to(w1_len.dtype).reshape(w1_len.shape)
+            g_w2 = g_small[WEC_HID: 2 * WEC_HID].to(w2.dtype).reshape(w2.shape)
+            g_b2 = g_small[2 * WEC_HID:].to(b2.dtype).reshape(b2.shape)
+            g_ew = None
+        else:
+            g_w1l = g_w2 = g_b2 = None
+            g_ew = g_w.reshape(ew_shape).to(ew_dtype)
+            if g_w_ext is not None:      # the reused weights are also returned: their own gradient passes through
+                g_ew = g_ew + g_w_ext.reshape(ew_shape).to(ew_dtype)
+        return None, None, None, g_x, None, g_wcat, g_bcat, g_w1l, g_w2, g_b2, g_ew
+
+
+def weighted_edge_conv(x, edge_index, pos, w1, b1, w2, b2, wt, bt, aggr: str, edge_weights=None,
+                       compute_weights: bool = True):
+    """Functional WeightedEdgeConv.forward (orig :173): returns (out [N,out], edge_weights [E,1])."""
+    ops._require_cuda(x, edge_index, pos, edge_weights)
+    if aggr not in ("add", "mean"):
+        raise ValueError(f"Unknown aggregation: {aggr}")
+    ops.dtype_code(x)
+    in_dim, out_dim = wt.size(1), wt.size(0)
+    if x.dim() != 2 or x.size(1) != in_dim:
+        raise RuntimeError(f"x must be [N, {in_dim}]")
+    if out_dim > 128 or out_dim % 4 or in_dim % 4:
+        raise RuntimeError("the sm_100a WeightedEdgeConv kernels need in_dim % 4 == 0 and out_dim % 4 == 0, out_dim <= 128 "
+                           f"(got {in_dim}, {out_dim})")
+    plan = ops.PLAN_CACHE.get(edge_index, x.size(0))
+    compute = bool(compute_weights) and edge_weights is None
+    if compute:
+        if pos is None:
+            raise RuntimeError("WeightedEdgeConv needs `pos` to compute edge weights")
+        w_cat = torch.cat([w1[:, :in_dim], w1[:, in_dim: 2 * in_dim], wt], dim=0)
+        b_cat = torch.cat([torch.zeros_like(b1), b1, bt])
+        w1_len = w1[:, 2 * in_dim]
+        pos32 = pos.detach().float().contiguous()
+        out, w = WecFn.apply(plan, aggr == "mean", out_dim, x, pos32, w_cat, b_cat, w1_len, w2.reshape(-1), b2, None)
+        return out, w
+    if edge_weights is None:
+        # the reference would fail at `x_transformed[src] * None`; say why
+        raise TypeError("WeightedEdgeConv: compute_weights=False needs edge_weights")
+    out, _ = WecFn.apply(plan, aggr == "mean", out_dim, x, None, wt, bt, None, None, None, edge_weights)
+    return out, edge_weights

@@ -177,4 +177,7 @@ int launch_agg_fixup(const float* part, const int32_t* rowptr, float* agg, int64
 // deterministic reduction of per-CTA weight-gradient partials: out[j] = sum_c part[c*stride + j]
 int launch_reduce_partials(const float* part, int n_parts, size_t stride, float* out, size_t n,
                            cudaStream_t st);
+// inclusive prefix sum of n int32 (sort_plan.cu); `out` may alias `in`; ws needs scan_ws_bytes(n)
+size_t scan_ws_bytes(int64_t n);
+int inclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* ws, cudaStream_t st);
 }  // namespace aero

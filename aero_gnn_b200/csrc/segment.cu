@@ -13,12 +13,13 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const T* __restrict__ 
   if (row >= n_out) return;
   int lane = threadIdx.x & 31;
   int64_t srow = idx ? (int64_t)idx[row] : row;
-  const T* ip = in + srow * width;
+  const bool hole = srow < 0;   // negative index = a zero row (Unpool: fine nodes that were not selected)
+  const T* ip = in + (hole ? 0 : srow) * width;
   T* op = out + row * width;
   const T* ap = add ? add + row * width : nullptr;
   if ((width & 3) == 0) {
     for (int c = lane * 4; c < width; c += 128) {
-      float4 v = load4(ip + c);
+      float4 v = hole ? make_float4(0.f, 0.f, 0.f, 0.f) : load4(ip + c);
       if (ap) {
         float4 a = load4(ap + c);
         v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
@@ -27,7 +28,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const T* __restrict__ 
     }
   } else {
     for (int c = lane; c < width; c += 32) {
-      float v = load1(ip + c);
+      float v = hole ? 0.f : load1(ip + c);
       if (ap) v += load1(ap + c);
       store1(op + c, v);
     }

@@ -210,10 +210,10 @@ __global__ void __launch_bounds__(SC_THREADS) scan_apply_kernel(const int32_t* _
   }
 }
 
-static size_t scan_ws_bytes(int64_t n) { return align_up((size_t)cdiv(n > 0 ? n : 1, SC_TILE) * sizeof(int32_t), 256); }
+size_t scan_ws_bytes(int64_t n) { return align_up((size_t)cdiv(n > 0 ? n : 1, SC_TILE) * sizeof(int32_t), 256); }
 
 // out may alias in
-static int inclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* ws, cudaStream_t st) {
+int inclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* ws, cudaStream_t st) {
   if (n <= 0) return AERO_OK;
   int nb = (int)cdiv(n, SC_TILE);
   int32_t* bs = reinterpret_cast<int32_t*>(ws);

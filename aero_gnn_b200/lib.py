@@ -34,6 +34,21 @@ class BlockDesc(C.Structure):
     ]
 
 
+class WecDesc(C.Structure):
+    """Mirror of struct aero_wec_desc (include/aero_gnn.h)."""
+
+    _fields_ = [
+        ("dtype", C.c_int32), ("mean", C.c_int32), ("compute_w", C.c_int32), ("pos_dim", C.c_int32),
+        ("N", C.c_int64), ("E", C.c_int64), ("out_dim", C.c_int64), ("ldq", C.c_int64),
+        ("Q", C.c_void_p), ("pos", C.c_void_p), ("w1_len", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("rowptr", C.c_void_p), ("src", C.c_void_p), ("dst", C.c_void_p), ("perm", C.c_void_p),
+        ("sptr", C.c_void_p), ("sperm", C.c_void_p),
+        ("w", C.c_void_p), ("out", C.c_void_p), ("g_out", C.c_void_p), ("g_w_ext", C.c_void_p),
+        ("dQ", C.c_void_p), ("g_w", C.c_void_p), ("g_small", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 # name -> (restype, argtypes); every symbol declared in include/aero_gnn.h
 SIGNATURES = {
     "aero_last_error": (C.c_char_p, []),
@@ -65,6 +80,17 @@ SIGNATURES = {
     "aero_coarsen_edges": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_void_p, C.c_size_t, C.c_void_p]),
     "aero_group_lists_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "aero_group_lists": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 3 + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "aero_bfs_levels_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "aero_bfs_levels": (C.c_int, [C.c_void_p] * 3 + [C.c_int64] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                  C.c_void_p]),
+    "aero_bistride_select_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "aero_bistride_select": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 3 + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "aero_filter_edges_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "aero_filter_edges": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64] + [C.c_void_p] * 3
+                          + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "aero_wec_workspace_bytes": (C.c_size_t, [C.POINTER(WecDesc), C.c_int]),
+    "aero_wec_fwd": (C.c_int, [C.POINTER(WecDesc), C.c_void_p]),
+    "aero_wec_bwd": (C.c_int, [C.POINTER(WecDesc), C.c_void_p]),
 }
 
 _lib = None

@@ -110,7 +110,8 @@ int aero_hash_u64(const void* data, int64_t nbytes, uint64_t* out, void* stream)
  * Row gathers / segmented reductions (deterministic, no atomics).
  * ------------------------------------------------------------------------------------------ */
 /* out[i,:] = in[idx[i],:]            (mgnLayer.py:40-41 node_attr[row]; bsms_mgn.py:306 unpool)
- * if add != NULL: out[i,:] = in[idx[i],:] + add[i,:]   (bsms_mgn.py:199-200 unpool + skip) */
+ * if add != NULL: out[i,:] = in[idx[i],:] + add[i,:]   (bsms_mgn.py:199-200 unpool + skip)
+ * idx[i] < 0 reads a zero row (Unpool.forward of bistride_ops, pyc orig :102: non-selected fine rows stay 0) */
 int aero_gather_rows(const void* in, const int32_t* idx, const void* add, void* out,
                      int64_t n_out, int64_t width, int dtype, void* stream);
 /* out[n,:] = scale(n) * sum_{k in [ptr[n],ptr[n+1])} in[list ? list[k] : k, :]
@@ -229,6 +230,72 @@ size_t aero_group_lists_workspace_bytes(int64_t n);
 int aero_group_lists(const int64_t* group_of, int64_t n, int64_t n_groups,
                      int32_t* gptr, int32_t* glist, int32_t* group32,
                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * BFS-bistride pooling and WeightedEdgeConv (the reference's bistride_ops module, shipped only as
+ * models/__pycache__/bistride_ops.cpython-311.pyc; "orig :NN" = first line of the code object in it).
+ * Index kernels are bit-exact (last row).
+ * ------------------------------------------------------------------------------------------ */
+/* BistridePooling.bfs_distance (orig :21): dist[v] = number of sender->receiver hops from `start`, -1 when
+ * unreachable.  sptr/sperm/dst = the sender-CSR of aero_graph_plan_build.  One kernel launch per BFS level; a call
+ * runs levels [level_begin, level_begin+level_count) and writes status[0] = size of the next frontier (0 = finished),
+ * status[1] = next level (device int64[2]).  level_begin == 0 initialises dist and the workspace; later calls must
+ * pass the same workspace.  Replaces the reference's Python deque loop with one .item() per edge. */
+size_t aero_bfs_levels_workspace_bytes(int64_t N);
+int aero_bfs_levels(const int32_t* sptr, const int32_t* sperm, const int32_t* dst, int64_t N, int64_t E,
+                    int64_t start, int64_t level_begin, int64_t level_count, int64_t* dist, int64_t* status,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* BistridePooling.select_bistride_nodes (orig :56) after the BFS: selected = ascending ids with even dist >= 0;
+ * if fewer than 0.3*N of them, every reached node instead.  index_map[i] = rank of i in `selected` or -1
+ * (MultiScaleGraphPreprocessor.create_multiscale_graph, bsms_mgn pyc orig :32).  counts[0] = number selected,
+ * counts[1] = 1 when the fallback fired (device int64[2]). */
+size_t aero_bistride_select_workspace_bytes(int64_t N);
+int aero_bistride_select(const int64_t* dist, int64_t N, int64_t* selected, int64_t* index_map, int64_t* counts,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* coarse edges of create_multiscale_graph (bsms_mgn pyc orig :32): edges whose two endpoints are selected, renumbered
+ * through index_map, self-loops dropped, caller order kept.  out_edge_index is [2,E] with row stride E (first
+ * counts[0] columns valid); kept_ids (optional) = caller edge id of each kept edge; counts[1] = out-of-range ids. */
+size_t aero_filter_edges_workspace_bytes(int64_t E);
+int aero_filter_edges(const int64_t* edge_index, int64_t E, const int64_t* index_map, int64_t N,
+                      int64_t* out_edge_index, int32_t* kept_ids, int64_t* counts,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* WeightedEdgeConv (orig :131-209):
+ *     len_e = || pos[dst_e] - pos[src_e] ||                                   (compute_edge_weights, orig :152)
+ *     w_e   = sigmoid( W2 relu( W1 [x[src_e] ; x[dst_e] ; len_e] + b1 ) + b2 )     hidden width 64
+ *     out[n] = sum (or mean) over edges e with dst_e == n of  w_e * (x[src_e] Wt^T + bt)      (forward, orig :173)
+ * The first Linear is split like the sum trick of mgnLayer.py:97-103: the caller pre-projects the node rows with one
+ * plain GEMM into Q = x [W1_src ; W1_dst ; Wt]^T + [0 ; b1 ; bt], row = [A(64) | B(64) | T(out_dim)], so an edge needs
+ * A[src] + B[dst] + w1_len * len.  With compute_w == 0 the weights are read from `w` (the weight reuse of the up pass,
+ * BSMSGMP.forward bsms_mgn pyc orig :145) and Q holds only T (ldq >= out_dim).
+ * Backward: dQ (same layout as Q) for the caller's GEMMs; compute_w: g_small = d(w1_len)[64] | d(W2)[64] | d(b2);
+ * otherwise g_w = gradient of the given weights.  g_w_ext = gradient arriving at the returned weights (may be NULL).
+ * Gradient w.r.t. pos is not produced.  Fixed accumulation order (receiver-CSR / sender-CSR), fp32 registers. */
+typedef struct aero_wec_desc {
+  int32_t dtype;      /* AERO_F32 | AERO_BF16: rows of Q, out, g_out, dQ and the weights w               */
+  int32_t mean;       /* aggr == 'mean'                                                                   */
+  int32_t compute_w;  /* 1: weights from the edge-weight MLP (written to w); 0: weights read from w       */
+  int32_t pos_dim;
+  int64_t N, E, out_dim, ldq;
+  const void* Q;      /* [N, ldq]                                                                         */
+  const float* pos;   /* [N, pos_dim] fp32 (compute_w)                                                    */
+  const float* w1_len;/* [64] fp32: last input column of edge_weight_mlp.0.weight                         */
+  const float* w2;    /* [64] fp32: edge_weight_mlp.2.weight                                              */
+  const float* b2;    /* [1]  fp32 (device)                                                               */
+  const int32_t *rowptr, *src, *dst, *perm, *sptr, *sperm;   /* graph plan                                */
+  void* w;            /* [E] caller edge order                                                            */
+  void* out;          /* fwd: [N, out_dim]                                                                */
+  const void* g_out;  /* bwd: [N, out_dim]                                                                */
+  const void* g_w_ext;/* bwd: optional [E] caller order                                                   */
+  void* dQ;           /* bwd: [N, ldq]                                                                    */
+  void* g_w;          /* bwd, compute_w == 0: [E] caller order                                            */
+  float* g_small;     /* bwd, compute_w == 1: [129] fp32                                                  */
+  void* workspace;
+  size_t workspace_bytes;
+} aero_wec_desc;
+size_t aero_wec_workspace_bytes(const aero_wec_desc* d, int backward);
+int aero_wec_fwd(const aero_wec_desc* d, void* stream);
+int aero_wec_bwd(const aero_wec_desc* d, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,334 @@
+"""GPU parity tests (-m gpu) of the BFS-bistride operators against oracle/bistride_oracle.py: BFS levels, node
+selection, coarse edge lists and unpool maps bit-exact; WeightedEdgeConv / GMP / BSMS_MeshGraphNet within 1e-5 relative
+(fp32 rows, gradients 1e-4) and 1e-2 relative (bf16 rows) -- the north_star tolerances."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err, rel_l2
+from oracle import bistride_oracle as B
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL, GTOL = 1e-5, 1e-4
+
+
+def _M():
+    import aero_gnn_b200.models as M
+    return M
+
+
+def _airfoil(nt=100, nr=50, seed=0):
+    from aero_gnn_b200.meshes import airfoil_o_mesh
+    m = airfoil_o_mesh(nt, nr, seed=seed)
+    g = torch.Generator().manual_seed(7)
+    pos = m.pos[:, :2].clone() + 1e-4 * torch.rand(m.pos.shape[0], 2, generator=g)   # no exact ties at the centroid
+    return m, pos
+
+
+def _random_graph(n, e, seed):
+    rng = np.random.default_rng(seed)
+    return torch.from_numpy(rng.integers(0, n, size=(2, e)).astype(np.int64))
+
+
+# ------------------------------------------------------------------------------------------------
+# integer kernels: bit-exact
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["airfoil", "random_sparse", "random_dense", "directed_chain", "single", "long_path"])
+def test_bfs_distance_bit_exact(case):
+    M = _M()
+    if case == "airfoil":
+        ei, n, starts = _airfoil()[0].edge_index, 5000, [0, 2500, 4999]
+    elif case == "random_sparse":      # many unreachable nodes, duplicates, self-loops
+        ei, n, starts = _random_graph(3000, 2500, 1), 3000, [0, 17, 2999]
+    elif case == "random_dense":
+        ei, n, starts = _random_graph(500, 20000, 2), 500, [3]
+    elif case == "directed_chain":
+        ei, n, starts = torch.stack([torch.arange(0, 299), torch.arange(1, 300)]), 300, [0, 150, 299]
+    elif case == "single":
+        ei, n, starts = torch.zeros((2, 1), dtype=torch.long), 1, [0]
+    else:                              # 1000 levels: several batches of BFS launches
+        a = torch.arange(0, 999)
+        ei, n, starts = torch.cat([torch.stack([a, a + 1]), torch.stack([a + 1, a])], 1), 1000, [0, 999]
+    for s in starts:
+        got = M.BistridePooling.bfs_distance(ei.to(DEV), n, s)
+        assert got.dtype == torch.int64
+        assert torch.equal(got.cpu(), B.bfs_distance(ei, n, s)), (case, s)
+
+
+def test_select_bistride_nodes_bit_exact():
+    M = _M()
+    m, pos = _airfoil()
+    for p in (pos, None):
+        got = M.BistridePooling.select_bistride_nodes(m.edge_index.to(DEV), 5000, None if p is None else p.to(DEV))
+        assert torch.equal(got.cpu(), B.select_bistride_nodes(m.edge_index, 5000, p))
+    # star: fallback to every reached node; the unreachable node 10 is dropped
+    pairs = [(0, k) for k in range(1, 10)]
+    ei = torch.tensor(pairs + [(b, a) for a, b in pairs]).t().contiguous()
+    got = M.BistridePooling.select_bistride_nodes(ei.to(DEV), 11)
+    assert got.cpu().tolist() == list(range(10)) == B.select_bistride_nodes(ei, 11).tolist()
+    ei = _random_graph(4000, 9000, 5)
+    assert torch.equal(M.BistridePooling.select_bistride_nodes(ei.to(DEV), 4000).cpu(), B.select_bistride_nodes(ei, 4000))
+
+
+@pytest.mark.parametrize("levels", [1, 3])
+def test_multiscale_hierarchy_bit_exact(levels):
+    M = _M()
+    m, pos = _airfoil()
+    data = types.SimpleNamespace(edge_index=m.edge_index.to(DEV), pos=pos.to(DEV))
+    got = M.MultiScaleGraphPreprocessor(levels).create_multiscale_graph(data)
+    ref = B.create_multiscale_graph(m.edge_index, pos, levels)
+    assert got["num_nodes"] == ref["num_nodes"]
+    for a, b in zip(got["node_indices"], ref["node_indices"]):
+        assert a.dtype == torch.int64 and torch.equal(a.cpu(), b)
+    for a, b in zip(got["edge_indices"], ref["edge_indices"]):
+        assert a.dtype == torch.int64 and torch.equal(a.cpu(), b)
+    for a, b in zip(got["positions"], ref["positions"]):
+        assert torch.equal(a.cpu(), b)
+    assert ref["num_nodes"][1] < 5000 and ref["edge_indices"][1].shape[1] > 0
+
+
+def test_filter_edges_edge_cases():
+    from aero_gnn_b200 import bistride as bs
+    imap = torch.tensor([0, -1, 1, 2, -1], device=DEV)
+    ei = torch.tensor([[0, 0, 2, 3, 1, 2, 3], [2, 0, 3, 0, 2, 1, 3]], device=DEV)   # self-loops, dropped endpoints
+    cei, kept = bs.filter_edges(ei, imap)
+    assert cei.cpu().tolist() == [[0, 1, 2], [1, 2, 0]] and kept.cpu().tolist() == [0, 2, 3]
+    cei, kept = bs.filter_edges(torch.zeros((2, 0), dtype=torch.long, device=DEV), imap)
+    assert cei.shape == (2, 0) and kept.numel() == 0
+    with pytest.raises(IndexError):
+        bs.filter_edges(torch.tensor([[0], [9]], device=DEV), imap)
+
+
+def test_unpool_exact_and_adjoint():
+    M = _M()
+    g = torch.Generator().manual_seed(0)
+    xc = torch.randn(40, 128, generator=g)
+    idx = torch.sort(torch.randperm(100, generator=g)[:40]).values
+    xd = xc.to(DEV).requires_grad_(True)
+    out = M.Unpool()(xd, idx.to(DEV), 100)
+    assert torch.equal(out.detach().cpu(), B.unpool(xc, idx, 100))
+    gout = torch.randn(100, 128, generator=g)
+    out.backward(gout.to(DEV))
+    assert torch.equal(xd.grad.cpu(), gout[idx])
+    out3 = M.Unpool()(xc.view(2, 20, 128).to(DEV), idx[:20].to(DEV), 100)
+    assert torch.equal(out3.cpu(), B.unpool(xc.view(2, 20, 128), idx[:20], 100))
+
+
+# ------------------------------------------------------------------------------------------------
+# WeightedEdgeConv
+# ------------------------------------------------------------------------------------------------
+def _wec_case(n, e, in_dim, out_dim, seed, pos_dim=2):
+    M = _M()
+    torch.manual_seed(seed)
+    mod = M.WeightedEdgeConv(in_dim, out_dim)
+    sd = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(n, in_dim, generator=g)
+    pos = torch.randn(n, pos_dim, generator=g)
+    ei = _random_graph(n, e, seed + 2)
+    return mod, sd, x, pos, ei
+
+
+@pytest.mark.parametrize("n,e,in_dim,out_dim,aggr,pos_dim", [(300, 2111, 128, 128, "add", 2), (50, 700, 128, 128, "mean", 3),
+                                                             (1000, 5000, 64, 32, "add", 2), (7, 0, 128, 128, "add", 2),
+                                                             (5000, 29600, 128, 128, "add", 2)])
+def test_wec_fp32_forward_backward_vs_oracle(n, e, in_dim, out_dim, aggr, pos_dim):
+    mod, sd, x, pos, ei = _wec_case(n, e, in_dim, out_dim, 3, pos_dim)
+    mod.aggr = aggr
+    mod = mod.to(DEV)
+    xd = x.to(DEV).requires_grad_(True)
+    out, w = mod(xd, ei.to(DEV), pos.to(DEV))
+    # oracle with autograd on CPU
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    oref, wref = B.wec(sdr, "", xr, ei, pos, aggr=aggr)
+    assert w.shape == (e, 1) and out.shape == (n, out_dim)
+    if e:
+        assert rel_err(w, wref) < TOL
+    assert rel_err(out, oref) < TOL if e else float(out.abs().max()) == 0.0
+    g = torch.Generator().manual_seed(9)
+    go, gw = torch.randn(n, out_dim, generator=g), torch.randn(e, 1, generator=g)
+    # the returned weights are used downstream too (the up pass reuses them): both gradients arrive
+    torch.autograd.backward([out, w], [go.to(DEV), gw.to(DEV)])
+    torch.autograd.backward([oref, wref], [go, gw])
+    if e == 0:
+        return
+    assert rel_err(xd.grad, xr.grad) < GTOL
+    for k, p in mod.named_parameters():
+        assert rel_err(p.grad, sdr[k].grad) < GTOL, k
+
+
+def test_wec_weight_reuse_vs_oracle():
+    mod, sd, x, pos, ei = _wec_case(400, 3000, 128, 128, 11)
+    mod = mod.to(DEV)
+    g = torch.Generator().manual_seed(1)
+    ew = torch.rand(3000, 1, generator=g)
+    xd, ewd = x.to(DEV).requires_grad_(True), ew.to(DEV).requires_grad_(True)
+    out, w_back = mod(xd, ei.to(DEV), pos.to(DEV), edge_weights=ewd, compute_weights=False)
+    assert w_back is ewd
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr, ewr = x.clone().requires_grad_(True), ew.clone().requires_grad_(True)
+    oref, _ = B.wec(sdr, "", xr, ei, pos, edge_weights=ewr, compute_weights=False)
+    assert rel_err(out, oref) < TOL
+    go = torch.randn(400, 128, generator=g)
+    out.backward(go.to(DEV))
+    oref.backward(go)
+    assert rel_err(xd.grad, xr.grad) < GTOL and rel_err(ewd.grad, ewr.grad) < GTOL
+    assert rel_err(mod.transform.weight.grad, sdr["transform.weight"].grad) < GTOL
+    assert rel_err(mod.transform.bias.grad, sdr["transform.bias"].grad) < GTOL
+    assert mod.edge_weight_mlp[0].weight.grad is None
+    with pytest.raises(ValueError, match="Unknown aggregation"):
+        mod.aggr = "max"
+        mod(xd, ei.to(DEV), pos.to(DEV))
+
+
+def test_wec_bf16_vs_fp32_oracle():
+    mod, sd, x, pos, ei = _wec_case(2000, 12000, 128, 128, 5)
+    mod = mod.to(DEV).to(torch.bfloat16)
+    sd16 = {k: v.detach().float().cpu() for k, v in mod.state_dict().items()}
+    x16 = x.to(torch.bfloat16)
+    xd = x16.to(DEV).requires_grad_(True)
+    out, w = mod(xd, ei.to(DEV), pos.to(DEV))
+    oref, wref = B.wec(sd16, "", x16.float(), ei, pos)
+    assert out.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert rel_l2(out.float(), oref) < 1e-2 and rel_l2(w.float(), wref) < 1e-2
+    out.float().square().mean().backward()
+    assert torch.isfinite(xd.grad.float()).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# GMP (one fused message-passing step, two-Linear MLPs) and the full model
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,e", [(300, 2111), (5000, 29600)])
+def test_gmp_fp32_forward_backward_vs_oracle(n, e):
+    M = _M()
+    torch.manual_seed(4)
+    mod = M.GMP(128, 128, 128)
+    sd = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+    g = torch.Generator().manual_seed(5)
+    x, ea = torch.randn(n, 128, generator=g), torch.randn(e, 128, generator=g)
+    ei = _random_graph(n, e, 6)
+    mod = mod.to(DEV)
+    xd, ed = x.to(DEV).requires_grad_(True), ea.to(DEV).requires_grad_(True)
+    xo, eo = mod(xd, ed, ei.to(DEV))
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr, er = x.clone().requires_grad_(True), ea.clone().requires_grad_(True)
+    xref, eref = B.gmp(sdr, "", xr, er, ei)
+    assert rel_err(xo, xref) < TOL and rel_err(eo, eref) < TOL
+    gx, ge = torch.randn(n, 128, generator=g), torch.randn(e, 128, generator=g)
+    torch.autograd.backward([xo, eo], [gx.to(DEV), ge.to(DEV)])
+    torch.autograd.backward([xref, eref], [gx, ge])
+    assert rel_err(xd.grad, xr.grad) < GTOL and rel_err(ed.grad, er.grad) < GTOL
+    for k, p in mod.named_parameters():
+        assert rel_err(p.grad, sdr[k].grad) < GTOL, k
+
+
+def test_gmp_bf16_tcgen05_vs_fp32_oracle():
+    M = _M()
+    from aero_gnn_b200 import lib, ops
+    torch.manual_seed(4)
+    mod = M.GMP(128, 128, 128).to(DEV).to(torch.bfloat16)
+    sd16 = {k: v.detach().float().cpu() for k, v in mod.state_dict().items()}
+    g = torch.Generator().manual_seed(5)
+    n, e = 5000, 29600
+    x, ea = torch.randn(n, 128, generator=g).bfloat16(), torch.randn(e, 128, generator=g).bfloat16()
+    ei = _random_graph(n, e, 6)
+    assert ops.choose_path(torch.bfloat16, "relu", 0) == lib.AERO_PATH_UMMA
+    xd, ed = x.to(DEV).requires_grad_(True), ea.to(DEV).requires_grad_(True)
+    xo, eo = mod(xd, ed, ei.to(DEV))
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd16.items()}
+    xr, er = x.float().requires_grad_(True), ea.float().requires_grad_(True)
+    xref, eref = B.gmp(sdr, "", xr, er, ei)
+    assert rel_l2(xo.float(), xref) < 1e-2 and rel_l2(eo.float(), eref) < 1e-2
+    gx = torch.randn(n, 128, generator=g).bfloat16()
+    xo.backward(gx.to(DEV))
+    xref.backward(gx.float())
+    assert rel_l2(xd.grad.float(), xr.grad) < 3e-2 and rel_l2(ed.grad.float(), er.grad) < 3e-2
+    for k, p in mod.named_parameters():
+        assert rel_l2(p.grad.float(), sdr[k].grad) < 3e-2, k
+
+
+def test_gmp_silu_is_rejected_loudly():
+    M = _M()
+    mod = M.GMP(128, 128, 128, activation="silu").to(DEV)
+    with pytest.raises(RuntimeError, match="SiLU"):
+        mod(torch.zeros(4, 128, device=DEV), torch.zeros(2, 128, device=DEV), torch.tensor([[0, 1], [1, 2]], device=DEV))
+
+
+@pytest.mark.parametrize("levels", [1, 3])
+def test_bsms_meshgraphnet_fp32_vs_oracle(levels):
+    M = _M()
+    m, pos = _airfoil()
+    torch.manual_seed(0)
+    net = M.BSMS_MeshGraphNet(6, 3, 4, num_levels=levels)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.to(DEV)
+    data = types.SimpleNamespace(edge_index=m.edge_index.to(DEV), pos=pos.to(DEV))
+    multi = M.MultiScaleGraphPreprocessor(levels).create_multiscale_graph(data)
+    with pytest.raises(ValueError, match="multi_data must be provided"):
+        net(m.node_attr.to(DEV), m.edge_attr.to(DEV), m.edge_index.to(DEV))
+    na = m.node_attr.to(DEV).requires_grad_(True)
+    out = net(na, m.edge_attr.to(DEV), m.edge_index.to(DEV), multi)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    nar = m.node_attr.clone().requires_grad_(True)
+    ref = B.bsms_meshgraphnet(sdr, levels, nar, m.edge_attr, B.create_multiscale_graph(m.edge_index, pos, levels))
+    assert out.shape == (5000, 4)
+    assert rel_err(out, ref) < 2e-5       # ~(2 levels + 2) GMP/WEC blocks deep: per-block error 1e-5 compounds
+    g = torch.Generator().manual_seed(3)
+    go = torch.randn(5000, 4, generator=g)
+    out.backward(go.to(DEV))
+    ref.backward(go)
+    assert rel_err(na.grad, nar.grad) < GTOL
+    used = 0
+    for k, p in net.named_parameters():
+        if sdr[k].grad is None:          # down_gmps[levels] is constructed but never called (orig :145)
+            assert p.grad is None and k.startswith(f"bsgmp.down_gmps.{levels}.")
+            continue
+        used += 1
+        assert rel_err(p.grad, sdr[k].grad) < 5e-4, k
+    assert used > 40
+
+
+def test_bsms_meshgraphnet_bf16_within_tolerance():
+    M = _M()
+    m, pos = _airfoil()
+    torch.manual_seed(0)
+    net = M.BSMS_MeshGraphNet(6, 3, 4, num_levels=2).to(DEV).to(torch.bfloat16)
+    sd16 = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
+    data = types.SimpleNamespace(edge_index=m.edge_index.to(DEV), pos=pos.to(DEV))
+    multi = M.MultiScaleGraphPreprocessor(2).create_multiscale_graph(data)
+    na16, ea16 = m.node_attr.bfloat16(), m.edge_attr.bfloat16()
+    out = net(na16.to(DEV), ea16.to(DEV), m.edge_index.to(DEV), multi)
+    ref = B.bsms_meshgraphnet(sd16, 2, na16.float(), ea16.float(), B.create_multiscale_graph(m.edge_index, pos, 2))
+    assert rel_l2(out.float(), ref) < 1e-2
+    out.float().square().mean().backward()
+    assert all(torch.isfinite(p.grad.float()).all() for p in net.parameters() if p.grad is not None)
+
+
+# ------------------------------------------------------------------------------------------------
+# full size (C5 mesh, 1M nodes / 6M edges): size-independent properties of the BFS hierarchy
+# ------------------------------------------------------------------------------------------------
+def test_bfs_hierarchy_properties_at_full_size():
+    from aero_gnn_b200 import bistride as bs, ops
+    from aero_gnn_b200.meshes import wing_surface_mesh
+    m = wing_surface_mesh(1000, 1000)
+    ei = m.edge_index.to(DEV)
+    n = m.pos.shape[0]
+    plan = ops.PLAN_CACHE.get(ei, n)
+    d = bs.bfs_levels(plan, 123456)
+    assert int(d.min()) == 0 and int((d == 0).sum()) == 1 and int(d[123456]) == 0      # connected mesh, one root
+    s, r = ei[0], ei[1]
+    assert int((d[r] - d[s]).abs().max()) <= 1                                           # undirected: levels differ by <= 1
+    # every non-root node has a neighbour one level closer
+    best = torch.full((n,), 1 << 40, dtype=torch.int64, device=DEV).scatter_reduce(0, r, d[s], "amin")
+    assert torch.equal(best[d > 0] + 1, d[d > 0])
+    sel, imap, fb = bs.bistride_select(d)
+    assert not fb and torch.equal(sel, torch.nonzero((d % 2) == 0).view(-1))
+    assert torch.equal(imap[sel], torch.arange(sel.numel(), device=DEV)) and int((imap >= 0).sum()) == sel.numel()
+    cei, kept = bs.filter_edges(ei, imap)
+    keep_ref = (imap[s] >= 0) & (imap[r] >= 0) & (s != r)
+    assert torch.equal(kept.long(), torch.nonzero(keep_ref).view(-1))
+    assert torch.equal(cei, torch.stack([imap[s[keep_ref]], imap[r[keep_ref]]]))
