@@ -184,15 +184,32 @@ __device__ __forceinline__ float edge_len(const float* __restrict__ pos, int pos
   return sqrtf(s);
 }
 
+// All three kernels walk a CSR segment in chunks of 32 slots: every lane first fetches the indices, the edge length,
+// the stored weight ... of ITS slot of the chunk (coalesced index loads, one gather latency for the whole chunk), then
+// the warp processes the slots in order, WEC_U at a time: the row gathers of WEC_U edges are issued together before
+// any of them is consumed, so a warp keeps WEC_U rows in flight instead of one (the kernels are latency-bound
+// gathers; the accumulation order stays slot by slot, i.e. deterministic).
+constexpr int WEC_U = 4;
+
+// logistic function with the hardware exp2 / reciprocal approximations (relative error ~1e-6, far inside the fp32
+// tolerance of 1e-5); the forward and the backward recompute use the same expression, so they agree bit for bit
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& t) {
+  acc.x = fmaf(w, t.x, acc.x); acc.y = fmaf(w, t.y, acc.y); acc.z = fmaf(w, t.z, acc.z); acc.w = fmaf(w, t.w, acc.w);
+}
+
 // forward: out[n] = sum_k w_k * T[src_k] over the receiver's CSR segment; w_k from the edge-weight MLP (COMPUTE) or given
 template <typename T, bool COMPUTE>
 __global__ void __launch_bounds__(WEC_THREADS) wec_fwd_kernel(WecArgs a) {
-  const int64_t n = (int64_t)blockIdx.x * (WEC_THREADS / 32) + (threadIdx.x >> 5);
+  // lane-0 broadcasts tell the compiler these values are warp-uniform: the loops below then need no per-shuffle
+  // reconvergence barriers
+  const int64_t n = (int64_t)blockIdx.x * (WEC_THREADS / 32) + __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   if (n >= a.N) return;
   const int lane = threadIdx.x & 31;
-  const T* Q = reinterpret_cast<const T*>(a.Q);
-  T* w = reinterpret_cast<T*>(a.w);
-  const int b = a.rowptr[n], e = a.rowptr[n + 1];
+  const T* __restrict__ Q = reinterpret_cast<const T*>(a.Q);
+  T* __restrict__ w = reinterpret_cast<T*>(a.w);
+  const int b = __shfl_sync(0xffffffffu, a.rowptr[n], 0), e = __shfl_sync(0xffffffffu, a.rowptr[n + 1], 0);
   const int c = lane * 4;
   const bool colok = c < a.out_dim;
   float2 Bn = make_float2(0.f, 0.f), wl = Bn, w2v = Bn;
@@ -204,25 +221,46 @@ __global__ void __launch_bounds__(WEC_THREADS) wec_fwd_kernel(WecArgs a) {
     b2v = a.b2[0];
   }
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k = b; k < e; ++k) {
-    const int64_t s = a.src[k];
-    const int pk = a.perm[k];
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (colok) t = load4(Q + s * a.ldq + a.toff + c);
-    float wgt;
-    if (COMPUTE) {
-      float2 As = load2(Q + s * a.ldq + 2 * lane);
-      const float len = edge_len(a.pos, a.pos_dim, s, n);
-      const float h0 = fmaxf(As.x + Bn.x + wl.x * len, 0.f);
-      const float h1 = fmaxf(As.y + Bn.y + wl.y * len, 0.f);
-      const float sc = warp_sum(h0 * w2v.x + h1 * w2v.y) + b2v;
-      wgt = round_to<T>(1.f / (1.f + expf(-sc)));
-      if (lane == 0) store1(w + pk, wgt);
-    } else {
-      wgt = load1(w + pk);
+  for (int base = b; base < e; base += 32) {
+    const int cnt = e - base < 32 ? e - base : 32;
+    int my_s = 0, my_p = 0;
+    float my_x = 0.f;   // COMPUTE: edge length of my slot; otherwise: the given weight of my slot
+    if (lane < cnt) {
+      my_s = a.src[base + lane];
+      my_p = a.perm[base + lane];
+      my_x = COMPUTE ? edge_len(a.pos, a.pos_dim, my_s, n) : load1(w + my_p);
     }
-    acc.x = fmaf(wgt, t.x, acc.x); acc.y = fmaf(wgt, t.y, acc.y);
-    acc.z = fmaf(wgt, t.z, acc.z); acc.w = fmaf(wgt, t.w, acc.w);
+    float my_w = my_x;
+    for (int j0 = 0; j0 < cnt; j0 += WEC_U) {
+      float4 t[WEC_U];
+      float2 As[WEC_U];
+#pragma unroll
+      for (int u = 0; u < WEC_U; ++u) {
+        const int64_t s = __shfl_sync(0xffffffffu, my_s, (j0 + u) & 31);
+        t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        As[u] = make_float2(0.f, 0.f);
+        if (j0 + u < cnt) {
+          if (colok) t[u] = load4(Q + s * a.ldq + a.toff + c);
+          if (COMPUTE) As[u] = load2(Q + s * a.ldq + 2 * lane);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < WEC_U; ++u) {
+        // slots past the end of the chunk carry zero rows (t = As = 0): they add nothing, so no branch is needed and
+        // the shuffles below stay in straight-line code
+        const float xv = __shfl_sync(0xffffffffu, my_x, (j0 + u) & 31);
+        float wgt = xv;
+        if (COMPUTE) {
+          const float h0 = fmaxf(As[u].x + Bn.x + wl.x * xv, 0.f);
+          const float h1 = fmaxf(As[u].y + Bn.y + wl.y * xv, 0.f);
+          const float sc = warp_sum(h0 * w2v.x + h1 * w2v.y) + b2v;
+          wgt = round_to<T>(sigmoid_fast(sc));
+          if (lane == j0 + u) my_w = wgt;
+        }
+        fma4(acc, wgt, t[u]);
+      }
+    }
+    if (COMPUTE && lane < cnt) store1(w + my_p, my_w);
   }
   if (a.mean) {
     const float cnt = (float)(e - b > 1 ? e - b : 1);
@@ -237,10 +275,10 @@ __global__ void __launch_bounds__(WEC_THREADS) wec_fwd_kernel(WecArgs a) {
 template <typename T, bool COMPUTE>
 __global__ void __launch_bounds__(WEC_THREADS) wec_bwd_recv_kernel(WecArgs a) {
   __shared__ float red[WEC_THREADS / 32][WEC_PART_LD];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const T* Q = reinterpret_cast<const T*>(a.Q);
-  const T* G = reinterpret_cast<const T*>(a.g_out);
-  const T* gwx = reinterpret_cast<const T*>(a.g_w_ext);
+  const int lane = threadIdx.x & 31, wid = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const T* __restrict__ Q = reinterpret_cast<const T*>(a.Q);
+  const T* __restrict__ G = reinterpret_cast<const T*>(a.g_out);
+  const T* __restrict__ gwx = reinterpret_cast<const T*>(a.g_w_ext);
   const int c = lane * 4;
   const bool colok = c < a.out_dim;
   float2 wl = make_float2(0.f, 0.f), w2v = wl;
@@ -254,7 +292,7 @@ __global__ void __launch_bounds__(WEC_THREADS) wec_bwd_recv_kernel(WecArgs a) {
   float db2 = 0.f;
   const int64_t warps = (int64_t)gridDim.x * (WEC_THREADS / 32);
   for (int64_t n = (int64_t)blockIdx.x * (WEC_THREADS / 32) + wid; n < a.N; n += warps) {
-    const int b = a.rowptr[n], e = a.rowptr[n + 1];
+    const int b = __shfl_sync(0xffffffffu, a.rowptr[n], 0), e = __shfl_sync(0xffffffffu, a.rowptr[n + 1], 0);
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     if (colok) g = load4(G + n * a.out_dim + c);
     if (a.mean) {
@@ -263,30 +301,56 @@ __global__ void __launch_bounds__(WEC_THREADS) wec_bwd_recv_kernel(WecArgs a) {
     }
     float2 Bn = make_float2(0.f, 0.f), dB = Bn;
     if (COMPUTE) Bn = load2(Q + n * a.ldq + WEC_HID + 2 * lane);
-    for (int k = b; k < e; ++k) {
-      const int64_t s = a.src[k];
-      const int pk = a.perm[k];
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (colok) t = load4(Q + s * a.ldq + a.toff + c);
-      float dw = warp_sum(t.x * g.x + t.y * g.y + t.z * g.z + t.w * g.w);
-      if (gwx) dw += load1(gwx + pk);
-      if (COMPUTE) {
-        float2 As = load2(Q + s * a.ldq + 2 * lane);
-        const float len = edge_len(a.pos, a.pos_dim, s, n);
-        const float h0 = fmaxf(As.x + Bn.x + wl.x * len, 0.f);
-        const float h1 = fmaxf(As.y + Bn.y + wl.y * len, 0.f);
-        const float sc = warp_sum(h0 * w2v.x + h1 * w2v.y) + b2v;
-        const float wgt = 1.f / (1.f + expf(-sc));
-        const float ds = dw * wgt * (1.f - wgt);
-        if (lane == 0) a.ds[k] = ds;
-        const float dz0 = h0 > 0.f ? ds * w2v.x : 0.f;
-        const float dz1 = h1 > 0.f ? ds * w2v.y : 0.f;
-        dB.x += dz0; dB.y += dz1;
-        dwl.x = fmaf(dz0, len, dwl.x); dwl.y = fmaf(dz1, len, dwl.y);
-        dw2.x = fmaf(ds, h0, dw2.x); dw2.y = fmaf(ds, h1, dw2.y);
-        db2 += ds;
-      } else {
-        if (lane == 0) store1(reinterpret_cast<T*>(a.g_w) + pk, dw);
+    for (int base = b; base < e; base += 32) {
+      const int cnt = e - base < 32 ? e - base : 32;
+      int my_s = 0, my_p = 0;
+      float my_len = 0.f, my_gw = 0.f, my_out = 0.f;
+      if (lane < cnt) {
+        my_s = a.src[base + lane];
+        my_p = a.perm[base + lane];
+        if (COMPUTE) my_len = edge_len(a.pos, a.pos_dim, my_s, n);
+        if (gwx) my_gw = load1(gwx + my_p);
+      }
+      for (int j0 = 0; j0 < cnt; j0 += WEC_U) {
+        float4 t[WEC_U];
+        float2 As[WEC_U];
+#pragma unroll
+        for (int u = 0; u < WEC_U; ++u) {
+          const int64_t s = __shfl_sync(0xffffffffu, my_s, (j0 + u) & 31);
+          t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          As[u] = make_float2(0.f, 0.f);
+          if (j0 + u < cnt) {
+            if (colok) t[u] = load4(Q + s * a.ldq + a.toff + c);
+            if (COMPUTE) As[u] = load2(Q + s * a.ldq + 2 * lane);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < WEC_U; ++u) {
+          // slots past the end of the chunk: t = As = 0 and gw = 0 give dw = ds = 0, every sum below gains 0
+          const float len = __shfl_sync(0xffffffffu, my_len, (j0 + u) & 31);
+          const float gw = __shfl_sync(0xffffffffu, my_gw, (j0 + u) & 31);
+          const float dw = warp_sum(t[u].x * g.x + t[u].y * g.y + t[u].z * g.z + t[u].w * g.w) + gw;
+          if (COMPUTE) {
+            const float h0 = fmaxf(As[u].x + Bn.x + wl.x * len, 0.f);
+            const float h1 = fmaxf(As[u].y + Bn.y + wl.y * len, 0.f);
+            const float sc = warp_sum(h0 * w2v.x + h1 * w2v.y) + b2v;
+            const float wgt = sigmoid_fast(sc);
+            const float ds = dw * wgt * (1.f - wgt);
+            if (lane == j0 + u) my_out = ds;
+            const float dz0 = h0 > 0.f ? ds * w2v.x : 0.f;
+            const float dz1 = h1 > 0.f ? ds * w2v.y : 0.f;
+            dB.x += dz0; dB.y += dz1;
+            dwl.x = fmaf(dz0, len, dwl.x); dwl.y = fmaf(dz1, len, dwl.y);
+            dw2.x = fmaf(ds, h0, dw2.x); dw2.y = fmaf(ds, h1, dw2.y);
+            db2 += ds;
+          } else {
+            if (lane == j0 + u) my_out = dw;
+          }
+        }
+      }
+      if (lane < cnt) {
+        if (COMPUTE) a.ds[base + lane] = my_out;                       // coalesced, CSR slot order
+        else store1(reinterpret_cast<T*>(a.g_w) + my_p, my_out);
       }
     }
     if (COMPUTE) store2(reinterpret_cast<T*>(a.dQ) + n * a.ldq + WEC_HID + 2 * lane, dB);
@@ -310,13 +374,13 @@ __global__ void __launch_bounds__(WEC_THREADS) wec_bwd_recv_kernel(WecArgs a) {
 // backward pass 2 (sender side): dT[s] = sum_k w_k g_out[dst_k];  COMPUTE: dA[s] = sum_k dz_k (dz recomputed from ds_k)
 template <typename T, bool COMPUTE>
 __global__ void __launch_bounds__(WEC_THREADS) wec_bwd_send_kernel(WecArgs a) {
-  const int64_t s = (int64_t)blockIdx.x * (WEC_THREADS / 32) + (threadIdx.x >> 5);
+  const int64_t s = (int64_t)blockIdx.x * (WEC_THREADS / 32) + __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   if (s >= a.N) return;
   const int lane = threadIdx.x & 31;
-  const T* Q = reinterpret_cast<const T*>(a.Q);
-  const T* G = reinterpret_cast<const T*>(a.g_out);
-  const T* w = reinterpret_cast<const T*>(a.w);
-  T* dQ = reinterpret_cast<T*>(a.dQ);
+  const T* __restrict__ Q = reinterpret_cast<const T*>(a.Q);
+  const T* __restrict__ G = reinterpret_cast<const T*>(a.g_out);
+  const T* __restrict__ w = reinterpret_cast<const T*>(a.w);
+  T* __restrict__ dQ = reinterpret_cast<T*>(a.dQ);
   const int c = lane * 4;
   const bool colok = c < a.out_dim;
   float2 As = make_float2(0.f, 0.f), wl = As, w2v = As, dA = As;
@@ -326,26 +390,49 @@ __global__ void __launch_bounds__(WEC_THREADS) wec_bwd_send_kernel(WecArgs a) {
     w2v = *reinterpret_cast<const float2*>(a.w2 + 2 * lane);
   }
   float4 dT = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int b = a.sptr[s], e = a.sptr[s + 1];
-  for (int j = b; j < e; ++j) {
-    const int k = a.sperm[j];
-    const int64_t n = a.dst[k];
-    const float wgt = load1(w + a.perm[k]);
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (colok) g = load4(G + n * a.out_dim + c);
-    if (a.mean) {
-      const int deg = a.rowptr[n + 1] - a.rowptr[n];
-      const float cnt = (float)(deg > 1 ? deg : 1);
-      g.x /= cnt; g.y /= cnt; g.z /= cnt; g.w /= cnt;
+  const int b = __shfl_sync(0xffffffffu, a.sptr[s], 0), e = __shfl_sync(0xffffffffu, a.sptr[s + 1], 0);
+  for (int base = b; base < e; base += 32) {
+    const int cnt = e - base < 32 ? e - base : 32;
+    int my_n = 0;
+    float my_w = 0.f, my_len = 0.f, my_ds = 0.f;
+    if (lane < cnt) {
+      const int k = a.sperm[base + lane];
+      my_n = a.dst[k];
+      my_w = load1(w + a.perm[k]);
+      if (COMPUTE) {
+        my_ds = a.ds[k];
+        my_len = edge_len(a.pos, a.pos_dim, s, my_n);
+      }
+      if (a.mean) {   // d out[n] / d msg = 1 / max(deg(n), 1): folded into the slot's weight, one division per slot
+        const int deg = a.rowptr[my_n + 1] - a.rowptr[my_n];
+        my_w /= (float)(deg > 1 ? deg : 1);
+      }
     }
-    dT.x = fmaf(wgt, g.x, dT.x); dT.y = fmaf(wgt, g.y, dT.y);
-    dT.z = fmaf(wgt, g.z, dT.z); dT.w = fmaf(wgt, g.w, dT.w);
-    if (COMPUTE) {
-      float2 Bn = load2(Q + n * a.ldq + WEC_HID + 2 * lane);
-      const float len = edge_len(a.pos, a.pos_dim, s, n);
-      const float ds = a.ds[k];
-      if (As.x + Bn.x + wl.x * len > 0.f) dA.x += ds * w2v.x;
-      if (As.y + Bn.y + wl.y * len > 0.f) dA.y += ds * w2v.y;
+    for (int j0 = 0; j0 < cnt; j0 += WEC_U) {
+      float4 g[WEC_U];
+      float2 Bn[WEC_U];
+#pragma unroll
+      for (int u = 0; u < WEC_U; ++u) {
+        const int64_t n = __shfl_sync(0xffffffffu, my_n, (j0 + u) & 31);
+        g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        Bn[u] = make_float2(0.f, 0.f);
+        if (j0 + u < cnt) {
+          if (colok) g[u] = load4(G + n * a.out_dim + c);
+          if (COMPUTE) Bn[u] = load2(Q + n * a.ldq + WEC_HID + 2 * lane);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < WEC_U; ++u) {
+        const float wgt = __shfl_sync(0xffffffffu, my_w, (j0 + u) & 31);
+        const float len = __shfl_sync(0xffffffffu, my_len, (j0 + u) & 31);
+        const float ds = __shfl_sync(0xffffffffu, my_ds, (j0 + u) & 31);
+        // slots past the end of the chunk: g = 0, wgt = ds = 0 -> nothing is added
+        fma4(dT, wgt, g[u]);
+        if (COMPUTE) {
+          if (As.x + Bn[u].x + wl.x * len > 0.f) dA.x += ds * w2v.x;
+          if (As.y + Bn[u].y + wl.y * len > 0.f) dA.y += ds * w2v.y;
+        }
+      }
     }
   }
   if (COMPUTE) store2(dQ + s * a.ldq + 2 * lane, dA);
@@ -416,7 +503,7 @@ extern "C" int aero_bfs_levels(const int32_t* sptr, const int32_t* sperm, const 
                                int64_t start, int64_t level_begin, int64_t level_count, int64_t* dist, int64_t* status,
                                void* workspace, size_t workspace_bytes, void* stream) {
   g_launch_count = 0;
-  AERO_CHECK_ARG(sptr && sperm && dst && dist && status && workspace, "aero_bfs_levels: null pointer");
+  AERO_CHECK_ARG(sptr && dist && status && workspace && (E == 0 || (sperm && dst)), "aero_bfs_levels: null pointer");
   AERO_CHECK_ARG(N > 0 && N < (1ll << 31) && E >= 0 && start >= 0 && start < N && level_begin >= 0 && level_count >= 0,
                  "aero_bfs_levels: bad sizes (N=%lld, start=%lld)", (long long)N, (long long)start);
   if (workspace_bytes < aero_bfs_levels_workspace_bytes(N)) {

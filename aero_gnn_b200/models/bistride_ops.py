@@ -126,10 +126,12 @@ class GMP(nn.Module):
         b_proj = torch.cat([torch.zeros_like(e0.bias), e0.bias, n0.bias]).to(dtype)
         return StepWeights(w_edge, w_node, w_proj, b_proj)
 
+    def forward_csr(self, x, e_csr, plan: ops.GraphPlan):
+        """The same step on edge rows already in the plan's receiver-CSR order; returns (x', e' in CSR order)."""
+        return run_stack(self.stack_config(), plan, x, e_csr, [self.step_weights(x.dtype)])
+
     def forward(self, x, edge_attr, edge_index):
         ops._require_cuda(x, edge_attr, edge_index)
-        cfg = self.stack_config()
         plan = ops.PLAN_CACHE.get(edge_index, x.size(0))
-        e_csr = permute_rows(edge_attr, plan.perm, plan.inv_perm)
-        x, e_csr = run_stack(cfg, plan, x, e_csr, [self.step_weights(x.dtype)])
+        x, e_csr = self.forward_csr(x, permute_rows(edge_attr, plan.perm, plan.inv_perm), plan)
         return x, permute_rows(e_csr, plan.inv_perm, plan.perm)

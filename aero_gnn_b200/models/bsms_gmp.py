@@ -16,6 +16,7 @@ from torch import nn
 
 from .. import bistride as _b
 from .. import ops
+from ..processor import permute_rows
 from .bistride_ops import GMP, BistridePooling, Unpool, WeightedEdgeConv, _index_maps
 from .mlp import MLP
 
@@ -61,18 +62,28 @@ class BSMSGMP(nn.Module):
                                            for _ in range(num_levels))
         self.unpools = nn.ModuleList(Unpool() for _ in range(num_levels))
 
-    def forward(self, x, edge_attrs, edge_indices, node_indices, num_nodes_list, positions):
-        edge_attrs = list(edge_attrs)
+    def _gmp(self, gmp: GMP, x, edge_attr, edge_index, in_csr_order: bool):
+        """One GMP step; the updated edge latents are dropped -- nothing downstream reads them (orig :145 returns x
+        only), so they are neither permuted back to the caller's edge order nor kept."""
+        ops._require_cuda(x, edge_attr, edge_index)
+        plan = ops.PLAN_CACHE.get(edge_index, x.size(0))
+        e_csr = edge_attr if in_csr_order else permute_rows(edge_attr, plan.perm, plan.inv_perm)
+        return gmp.forward_csr(x, e_csr, plan)[0]
+
+    def forward(self, x, edge_attrs, edge_indices, node_indices, num_nodes_list, positions,
+                edges_in_csr_order: bool = False):
+        """`edges_in_csr_order` (extension, used by BSMS_MeshGraphNet): edge_attrs[i] rows are already in the
+        receiver-CSR order of ops.PLAN_CACHE.get(edge_indices[i], n_i) instead of the caller's edge order."""
         skips, weights_down = [], []
         for i in range(self.num_levels):
-            x, edge_attrs[i] = self.down_gmps[i](x, edge_attrs[i], edge_indices[i])
+            x = self._gmp(self.down_gmps[i], x, edge_attrs[i], edge_indices[i], edges_in_csr_order)
             skips.append(x)                                    # the reference clones; nothing here writes in place
             x_conv, ew = self.down_edge_convs[i](x, edge_indices[i], positions[i], compute_weights=True)
             weights_down.append(ew)
             x = x + x_conv
             sel32, imap = _index_maps(node_indices[i], int(num_nodes_list[i]))
             x = _b.SelectRowsFn.apply(x, sel32, imap)          # x[node_indices[i]]
-        x, edge_attrs[-1] = self.bottom_gmp(x, edge_attrs[-1], edge_indices[-1])
+        x = self._gmp(self.bottom_gmp, x, edge_attrs[-1], edge_indices[-1], edges_in_csr_order)
         for i in range(self.num_levels - 1, -1, -1):
             x = self.unpools[i](x, node_indices[i], num_nodes_list[i])
             x_conv, _ = self.up_edge_convs[i](x, edge_indices[i], positions[i], edge_weights=weights_down[i],
@@ -102,16 +113,19 @@ class BSMS_MeshGraphNet(nn.Module):
 
     def forward(self, node_attr, edge_attr, edge_index, multi_data=None):
         ops._require_cuda(node_attr, edge_attr, edge_index)
-        node_hidden = self.node_encoder(node_attr)
-        edge_hidden = self.edge_encoder(edge_attr)
         if multi_data is None:
             raise ValueError("multi_data must be provided. Use MultiScaleGraphPreprocessor to create it.")
+        node_hidden = self.node_encoder(node_attr)
+        # raw edge features go into receiver-CSR order once, before the encoder (a few columns per edge instead of a
+        # 128-wide latent row per GMP call); coarse-level edge latents start as zeros, which any order leaves unchanged
+        plan0 = ops.PLAN_CACHE.get(multi_data["edge_indices"][0], node_attr.size(0))
+        edge_hidden = self.edge_encoder(permute_rows(edge_attr, plan0.perm, plan0.inv_perm))
         edge_attrs = [edge_hidden]
         for i in range(1, len(multi_data["edge_indices"])):
             num_edges = multi_data["edge_indices"][i].shape[1]
             edge_attrs.append(torch.zeros(num_edges, self.latent_dim, device=edge_hidden.device, dtype=edge_hidden.dtype))
         x = self.bsgmp(node_hidden, edge_attrs, multi_data["edge_indices"], multi_data["node_indices"],
-                       multi_data["num_nodes"], multi_data["positions"])
+                       multi_data["num_nodes"], multi_data["positions"], edges_in_csr_order=True)
         return self.decoder(x)
 
 

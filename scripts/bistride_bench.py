@@ -23,6 +23,7 @@ from aero_gnn_b200.meshes import airfoil_o_mesh, wing_surface_mesh
 
 which = sys.argv[1] if len(sys.argv) > 1 else "c3"
 dt = torch.bfloat16 if (len(sys.argv) < 3 or sys.argv[2] == "bf16") else torch.float32
+PROF = len(sys.argv) > 3 and sys.argv[3] == "prof"    # one launch of each kernel, no warm-up: for an ncu capture
 dev = torch.device("cuda", 0)
 mesh = airfoil_o_mesh(400, 250, seed=0) if which == "c3" else wing_surface_mesh(1000, 1000)
 pos = mesh.pos[:, :2].contiguous().to(dev)
@@ -35,6 +36,8 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
 def timed(fn, n=20, warm=5):
+    if PROF:
+        n, warm = 1, 0
     for _ in range(warm):
         fn()
     ts = []

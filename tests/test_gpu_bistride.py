@@ -36,7 +36,8 @@ def _random_graph(n, e, seed):
 # ------------------------------------------------------------------------------------------------
 # integer kernels: bit-exact
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("case", ["airfoil", "random_sparse", "random_dense", "directed_chain", "single", "long_path"])
+@pytest.mark.parametrize("case", ["airfoil", "random_sparse", "random_dense", "directed_chain", "single", "no_edges",
+                                  "long_path"])
 def test_bfs_distance_bit_exact(case):
     M = _M()
     if case == "airfoil":
@@ -49,6 +50,8 @@ def test_bfs_distance_bit_exact(case):
         ei, n, starts = torch.stack([torch.arange(0, 299), torch.arange(1, 300)]), 300, [0, 150, 299]
     elif case == "single":
         ei, n, starts = torch.zeros((2, 1), dtype=torch.long), 1, [0]
+    elif case == "no_edges":
+        ei, n, starts = torch.zeros((2, 0), dtype=torch.long), 5, [3]
     else:                              # 1000 levels: several batches of BFS launches
         a = torch.arange(0, 999)
         ei, n, starts = torch.cat([torch.stack([a, a + 1]), torch.stack([a + 1, a])], 1), 1000, [0, 999]
@@ -148,7 +151,7 @@ def test_wec_fp32_forward_backward_vs_oracle(n, e, in_dim, out_dim, aggr, pos_di
     assert w.shape == (e, 1) and out.shape == (n, out_dim)
     if e:
         assert rel_err(w, wref) < TOL
-    assert rel_err(out, oref) < TOL if e else float(out.abs().max()) == 0.0
+    assert rel_err(out, oref) < TOL if e else float(out.detach().abs().max()) == 0.0
     g = torch.Generator().manual_seed(9)
     go, gw = torch.randn(n, out_dim, generator=g), torch.randn(e, 1, generator=g)
     # the returned weights are used downstream too (the up pass reuses them): both gradients arrive
@@ -202,8 +205,30 @@ def test_wec_bf16_vs_fp32_oracle():
 # ------------------------------------------------------------------------------------------------
 # GMP (one fused message-passing step, two-Linear MLPs) and the full model
 # ------------------------------------------------------------------------------------------------
+def _gmp_grads(sd, x, ea, ei, gx, ge, dt):  # noqa: E302
+    """Oracle autograd of GMP in dtype `dt`: (x', e', [g_x, g_e, g_params...])."""
+    sdr = {k: v.to(dt).clone().requires_grad_(True) for k, v in sd.items()}
+    xr, er = x.to(dt).clone().requires_grad_(True), ea.to(dt).clone().requires_grad_(True)
+    xo, eo = B.gmp(sdr, "", xr, er, ei)
+    grads = torch.autograd.grad([xo, eo], [xr, er] + [sdr[k] for k in sd], [gx.to(dt), ge.to(dt)])
+    return xo, eo, grads
+
+
+def _rows_off(a, ref, tol=GTOL):
+    """Rows of `a` further than tol * max|ref| from `ref` (max-norm per row)."""
+    a, ref = a.detach().double().cpu().reshape(ref.shape[0], -1), ref.double().reshape(ref.shape[0], -1)
+    return int(((a - ref).abs().max(dim=1).values > tol * ref.abs().max()).sum())
+
+
 @pytest.mark.parametrize("n,e", [(300, 2111), (5000, 29600)])
 def test_gmp_fp32_forward_backward_vs_oracle(n, e):
+    """Forward <= 1e-5 against the fp32 oracle.  Gradients against the fp64 oracle: <= 1e-4 (max-norm) on every row but a
+    handful.  The first Linear is evaluated as e W_e^T + P_s[src] + P_d[dst] (sum trick), the oracle as one GEMM over
+    the concatenated row; of the E*128 = 3.8 M first pre-activations about one lies within fp32 rounding of zero, its
+    ReLU gate then differs between the two (equally valid) fp32 evaluations and the gradient rows of that one edge and
+    of its two end nodes move by a finite amount (scripts/diag_gmp_grads.py shows exactly that: one edge, its sender
+    and its receiver, everything else at 1e-6; the L=2 golden layer behaves the same).  So: at most 4 rows off, and
+    the whole tensor within 2e-3 in relative L2."""
     M = _M()
     torch.manual_seed(4)
     mod = M.GMP(128, 128, 128)
@@ -211,19 +236,19 @@ def test_gmp_fp32_forward_backward_vs_oracle(n, e):
     g = torch.Generator().manual_seed(5)
     x, ea = torch.randn(n, 128, generator=g), torch.randn(e, 128, generator=g)
     ei = _random_graph(n, e, 6)
+    gx, ge = torch.randn(n, 128, generator=g), torch.randn(e, 128, generator=g)
     mod = mod.to(DEV)
     xd, ed = x.to(DEV).requires_grad_(True), ea.to(DEV).requires_grad_(True)
     xo, eo = mod(xd, ed, ei.to(DEV))
-    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    xr, er = x.clone().requires_grad_(True), ea.clone().requires_grad_(True)
-    xref, eref = B.gmp(sdr, "", xr, er, ei)
+    xref, eref, _ = _gmp_grads(sd, x, ea, ei, gx, ge, torch.float32)
+    _, _, g64 = _gmp_grads(sd, x, ea, ei, gx, ge, torch.float64)
     assert rel_err(xo, xref) < TOL and rel_err(eo, eref) < TOL
-    gx, ge = torch.randn(n, 128, generator=g), torch.randn(e, 128, generator=g)
     torch.autograd.backward([xo, eo], [gx.to(DEV), ge.to(DEV)])
-    torch.autograd.backward([xref, eref], [gx, ge])
-    assert rel_err(xd.grad, xr.grad) < GTOL and rel_err(ed.grad, er.grad) < GTOL
-    for k, p in mod.named_parameters():
-        assert rel_err(p.grad, sdr[k].grad) < GTOL, k
+    got = [xd.grad, ed.grad] + [p.grad for _, p in mod.named_parameters()]
+    assert [k for k, _ in mod.named_parameters()] == list(sd)
+    for name, a, r64 in zip(["x", "e"] + list(sd), got, g64):
+        assert rel_l2(a, r64) < 2e-3, (name, rel_l2(a, r64))
+        assert _rows_off(a, r64) <= 4, (name, _rows_off(a, r64), rel_err(a, r64))
 
 
 def test_gmp_bf16_tcgen05_vs_fp32_oracle():
@@ -245,10 +270,17 @@ def test_gmp_bf16_tcgen05_vs_fp32_oracle():
     assert rel_l2(xo.float(), xref) < 1e-2 and rel_l2(eo.float(), eref) < 1e-2
     gx = torch.randn(n, 128, generator=g).bfloat16()
     xo.backward(gx.to(DEV))
-    xref.backward(gx.float())
-    assert rel_l2(xd.grad.float(), xr.grad) < 3e-2 and rel_l2(ed.grad.float(), er.grad) < 3e-2
-    for k, p in mod.named_parameters():
-        assert rel_l2(p.grad.float(), sdr[k].grad) < 3e-2, k
+    names = list(sd16)
+    ref = torch.autograd.grad(xref, [xr, er] + [sdr[k] for k in names], gx.float())
+    # yardstick: the same module evaluated by pure bf16 autograd (the reference's bf16 mode, train.py:30-33)
+    sdq = {k: v.bfloat16().requires_grad_(True) for k, v in sd16.items()}
+    xq, eq = x.clone().requires_grad_(True), ea.clone().requires_grad_(True)
+    xoq, _ = B.gmp(sdq, "", xq, eq, ei)
+    refq = torch.autograd.grad(xoq, [xq, eq] + [sdq[k] for k in names], gx)
+    got = [xd.grad, ed.grad] + [p.grad for _, p in mod.named_parameters()]
+    for name, a, r, q in zip(["x", "e"] + names, got, ref, refq):
+        ours, theirs = rel_l2(a.float(), r), rel_l2(q.float(), r)
+        assert ours <= max(1e-2, 2.0 * theirs), (name, ours, theirs)
 
 
 def test_gmp_silu_is_rejected_loudly():
@@ -281,15 +313,47 @@ def test_bsms_meshgraphnet_fp32_vs_oracle(levels):
     go = torch.randn(5000, 4, generator=g)
     out.backward(go.to(DEV))
     ref.backward(go)
-    assert rel_err(na.grad, nar.grad) < GTOL
+    # fp64 truth for the gradient yardstick (see test_gmp_fp32_forward_backward_vs_oracle)
+    sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    na64 = m.node_attr.double().requires_grad_(True)
+    mref = B.create_multiscale_graph(m.edge_index, pos, levels)
+    mref["positions"] = [p.double() for p in mref["positions"]]
+    ref64 = B.bsms_meshgraphnet(sd64, levels, na64, m.edge_attr.double(), mref)
+    ref64.backward(go.double())
+    g64 = {k: v.grad for k, v in sd64.items()}
+    assert rel_err(na.grad, na64.grad) < max(GTOL, 3 * rel_err(nar.grad, na64.grad))
     used = 0
     for k, p in net.named_parameters():
-        if sdr[k].grad is None:          # down_gmps[levels] is constructed but never called (orig :145)
-            assert p.grad is None and k.startswith(f"bsgmp.down_gmps.{levels}.")
+        if sdr[k].grad is None:
+            # constructed but never used (orig :145): down_gmps[levels], and the up convs' own edge-weight MLPs
+            # (the up pass reuses the down pass's weights)
+            assert p.grad is None and (k.startswith(f"bsgmp.down_gmps.{levels}.") or
+                                       (k.startswith("bsgmp.up_edge_convs.") and ".edge_weight_mlp." in k)), k
             continue
         used += 1
-        assert rel_err(p.grad, sdr[k].grad) < 5e-4, k
+        assert rel_err(p.grad, sdr[k].grad) < max(5e-4, 3 * rel_err(sdr[k].grad, g64[k])), k
     assert used > 40
+
+
+def test_bsmsgmp_public_forward_takes_caller_order_edges():
+    """BSMSGMP.forward called directly (edge latents in the caller's edge order, as the bytecode's signature has it)."""
+    M = _M()
+    m, pos = _airfoil(60, 30)
+    n, e = m.pos.shape[0], m.edge_index.shape[1]
+    torch.manual_seed(1)
+    mod = M.BSMSGMP(2, 128, 128)
+    sd = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+    mod = mod.to(DEV)
+    multi_ref = B.create_multiscale_graph(m.edge_index, pos, 2)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(n, 128, generator=g)
+    eas = [torch.randn(ei.shape[1], 128, generator=g) for ei in multi_ref["edge_indices"]]
+    ref = B.bsmsgmp(sd, "", 2, x, eas, multi_ref["edge_indices"], multi_ref["node_indices"], multi_ref["num_nodes"],
+                    multi_ref["positions"])
+    dev = lambda ts: [t.to(DEV) for t in ts]
+    out = mod(x.to(DEV), dev(eas), dev(multi_ref["edge_indices"]), dev(multi_ref["node_indices"]),
+              multi_ref["num_nodes"], dev(multi_ref["positions"]))
+    assert rel_err(out, ref) < 2e-5
 
 
 def test_bsms_meshgraphnet_bf16_within_tolerance():
