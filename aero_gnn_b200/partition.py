@@ -84,7 +84,8 @@ class HaloExchanger:
         self.send_idx = [torch.from_numpy(ix).to(device) for ix in plan.send_idx]
         self.recv_off = np.concatenate([[0], np.cumsum(plan.recv_counts)]).astype(int)
 
-    def _p2p(self, sends: Sequence[Optional[torch.Tensor]], recvs: Sequence[Optional[torch.Tensor]]) -> None:
+    def _post(self, sends: Sequence[Optional[torch.Tensor]], recvs: Sequence[Optional[torch.Tensor]]):
+        """Post all receives and sends; returns the outstanding requests (the buffers must outlive them)."""
         p2p = []
         for p in range(self.plan.world):
             if recvs[p] is not None and recvs[p].numel():
@@ -92,30 +93,51 @@ class HaloExchanger:
         for p in range(self.plan.world):
             if sends[p] is not None and sends[p].numel():
                 p2p.append(dist.P2POp(dist.isend, sends[p], p, self.group))
-        if p2p:
-            for req in dist.batch_isend_irecv(p2p):
-                req.wait()
+        return dist.batch_isend_irecv(p2p) if p2p else []
 
-    def forward(self, x_own: torch.Tensor) -> torch.Tensor:
-        """Rows of the remote senders, [n_halo, width], in halo order."""
+    # ---- split-phase API: post, do independent work on the compute stream, then finish ----------------------
+    def forward_start(self, x_own: torch.Tensor, out: Optional[torch.Tensor] = None):
+        """Post the exchange of the remote senders' rows into `out` ([n_halo, width], halo order; allocated when
+        None).  Returns a token for forward_finish(); `out` is valid only after it."""
         pl = self.plan
-        halo = x_own.new_empty((pl.n_halo, x_own.size(1)))
+        halo = out if out is not None else x_own.new_empty((pl.n_halo, x_own.size(1)))
         sends = [x_own[ix].contiguous() if ix.numel() else None for ix in self.send_idx]
         recvs = [halo[self.recv_off[p]: self.recv_off[p + 1]] if pl.recv_counts[p] else None for p in range(pl.world)]
-        self._p2p(sends, recvs)
+        return halo, sends, self._post(sends, recvs)
+
+    @staticmethod
+    def forward_finish(token) -> torch.Tensor:
+        halo, _sends, reqs = token
+        for req in reqs:
+            req.wait()
         return halo
 
-    def backward(self, g_halo: torch.Tensor, g_own: torch.Tensor) -> None:
-        """Send halo-row gradients back to their owners; owners add them in ascending peer order (deterministic:
-        the rows one peer returns are distinct)."""
+    def backward_start(self, g_halo: torch.Tensor, like: torch.Tensor):
+        """Post the return of the halo-row gradients to their owners (`like`: a tensor of the owners' dtype/device)."""
         pl = self.plan
         sends = [g_halo[self.recv_off[p]: self.recv_off[p + 1]].contiguous() if pl.recv_counts[p] else None
                  for p in range(pl.world)]
-        recvs = [g_own.new_empty((ix.numel(), g_own.size(1))) if ix.numel() else None for ix in self.send_idx]
-        self._p2p(sends, recvs)
-        for p in range(pl.world):
+        recvs = [like.new_empty((ix.numel(), like.size(1))) if ix.numel() else None for ix in self.send_idx]
+        return sends, recvs, self._post(sends, recvs)
+
+    def backward_finish(self, token, g_own: torch.Tensor) -> None:
+        """Owners add the returned rows in ascending peer order (deterministic: the rows one peer returns are
+        distinct)."""
+        _sends, recvs, reqs = token
+        for req in reqs:
+            req.wait()
+        for p in range(self.plan.world):
             if recvs[p] is not None:
                 g_own.index_add_(0, self.send_idx[p], recvs[p])
+
+    # ---- blocking forms ------------------------------------------------------------------------------------
+    def forward(self, x_own: torch.Tensor) -> torch.Tensor:
+        """Rows of the remote senders, [n_halo, width], in halo order."""
+        return self.forward_finish(self.forward_start(x_own))
+
+    def backward(self, g_halo: torch.Tensor, g_own: torch.Tensor) -> None:
+        """Send halo-row gradients back to their owners and accumulate them into g_own."""
+        self.backward_finish(self.backward_start(g_halo, g_own), g_own)
 
 
 class PartitionedStackFn(torch.autograd.Function):
@@ -133,13 +155,22 @@ class PartitionedStackFn(torch.autograd.Function):
         paths_bwd = (ops.choose_path(x.dtype, cfg.act_edge, cfg.L_edge, backward=True),
                      ops.choose_path(x.dtype, cfg.act_node, cfg.L_node, backward=True))
         keep_h0 = ops.keeps_h0(path_e, path_n, *paths_bwd)
-        saved = []
+        saved, preps = [], []
         for k in range(K):
             w_edge, w_node, w_proj, b_proj = flat[4 * k: 4 * k + 4]
             pe = ops.PreparedBlock(w_edge.detach(), cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
             pn = ops.PreparedBlock(w_node.detach(), cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
-            x_ext = torch.cat([x, ex.forward(x)], dim=0)
-            P = torch.addmm(b_proj.detach(), x_ext, w_proj.detach().t())
+            preps.append((pe, pn))
+            # the halo rows travel while the own rows are copied and pre-projected (no dependence on the exchange)
+            x_ext = x.new_empty((plan.N, D))
+            tok = ex.forward_start(x, out=x_ext[n_own:])
+            x_ext[:n_own].copy_(x)
+            P = x.new_empty((plan.N, w_proj.size(0)))
+            wt, bp = w_proj.detach().t(), b_proj.detach()
+            torch.addmm(bp, x, wt, out=P[:n_own])
+            ex.forward_finish(tok)
+            if plan.N > n_own:
+                torch.addmm(bp, x_ext[n_own:], wt, out=P[n_own:])
             h0e = torch.empty_like(e) if keep_h0 else None
             h0n = torch.empty_like(x) if keep_h0 else None
             e_new, agg = ops.block_fwd(pe, e, e, P, plan.src, plan.dst, 0, D, rowptr=plan.rowptr, want_agg=True,
@@ -153,6 +184,8 @@ class PartitionedStackFn(torch.autograd.Function):
         ctx.cfg, ctx.part, ctx.K = cfg, part, K
         ctx.set_materialize_grads(False)
         ctx.paths, ctx.keep_h0 = paths_bwd, keep_h0
+        # the weight images of the forward serve the backward too when both run on the same kernel family
+        ctx.preps = preps if (path_e, path_n) == paths_bwd else None
         ctx.save_for_backward(*saved, *flat)
         return x, e
 
@@ -173,8 +206,11 @@ class PartitionedStackFn(torch.autograd.Function):
             P, h0e, h0n = (None, a1, a2) if ctx.keep_h0 else (a1, None, None)
             x = x_ext[:n_own]
             w_edge, w_node, w_proj, b_proj = flat[4 * k: 4 * k + 4]
-            pe = ops.PreparedBlock(w_edge, cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
-            pn = ops.PreparedBlock(w_node, cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
+            if ctx.preps is not None:
+                pe, pn = ctx.preps[k]
+            else:
+                pe = ops.PreparedBlock(w_edge, cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
+                pn = ops.PreparedBlock(w_node, cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
             g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale, kind="node_bwd",
                                                h0=h0n, n_nodes=plan.N)
             agg_eff = agg if scale is None else agg * scale[:, None]
@@ -186,11 +222,12 @@ class PartitionedStackFn(torch.autograd.Function):
             ops.segment_reduce(g_h0e, plan.sptr, plan.sperm, plan.N, out=g_psd[:, :D])
             ops.segment_reduce(g_h0e, plan.rowptr, None, plan.N, out=g_psd[:, D:])
             g_ext = g_psd @ w_proj[:2 * D]                          # [n_local, D]
+            tok = ex.backward_start(g_ext[n_own:], g_ext)           # halo-row gradients travel under the GEMMs below
             g_x = G_x + g_ext[:n_own]
             g_x.addmm_(g_h0n, w_proj[2 * D:])
-            ex.backward(g_ext[n_own:], g_x)
             g_wproj = torch.cat([g_psd.t() @ x_ext, g_h0n.t() @ x], dim=0)
             g_bproj = torch.cat([g_we[-D:], g_we[-D:], g_wn[-D:]])
+            ex.backward_finish(tok, g_x)
             grads[4 * k: 4 * k + 4] = [g_we, g_wn, g_wproj.to(w_proj.dtype), g_bproj.to(b_proj.dtype)]
             G_x = g_x
         return (None, None, G_x, G_e, *grads)
@@ -230,8 +267,9 @@ class PartitionedProcessor:
             return
         flat = torch.cat([p.grad.reshape(-1).float() for p in ps])
         dist.all_reduce(flat, group=self.group)
-        off = 0
+        views, off = [], 0
         for p in ps:
             n = p.numel()
-            p.grad.copy_(flat[off: off + n].view_as(p.grad))
+            views.append(flat[off: off + n].view_as(p.grad))
             off += n
+        torch._foreach_copy_([p.grad for p in ps], views)      # one multi-tensor kernel instead of one copy per parameter

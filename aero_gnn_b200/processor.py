@@ -78,11 +78,12 @@ class MGNStackFn(torch.autograd.Function):
         paths_bwd = (ops.choose_path(x.dtype, cfg.act_edge, cfg.L_edge, backward=True),
                      ops.choose_path(x.dtype, cfg.act_node, cfg.L_node, backward=True))
         keep_h0 = ops.keeps_h0(path_e, path_n, *paths_bwd)
-        saved = []
+        saved, preps = [], []
         for k in range(K):
             w_edge, w_node, w_proj, b_proj = flat[4 * k: 4 * k + 4]
             pe = ops.PreparedBlock(w_edge.detach(), cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
             pn = ops.PreparedBlock(w_node.detach(), cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
+            preps.append((pe, pn))
             P = torch.addmm(b_proj.detach(), x, w_proj.detach().t())
             h0e = torch.empty_like(e) if keep_h0 else None
             h0n = torch.empty_like(x) if keep_h0 else None
@@ -97,6 +98,8 @@ class MGNStackFn(torch.autograd.Function):
         ctx.cfg, ctx.plan, ctx.K = cfg, plan, K
         ctx.set_materialize_grads(False)
         ctx.paths, ctx.keep_h0 = paths_bwd, keep_h0
+        # the weight images of the forward serve the backward too when both run on the same kernel family
+        ctx.preps = preps if (path_e, path_n) == paths_bwd else None
         ctx.save_for_backward(*saved, *flat)
         return x, e
 
@@ -116,8 +119,11 @@ class MGNStackFn(torch.autograd.Function):
             x, e, agg, a1, a2 = acts[5 * k: 5 * k + 5]
             P, h0e, h0n = (None, a1, a2) if ctx.keep_h0 else (a1, None, None)
             w_edge, w_node, w_proj, b_proj = flat[4 * k: 4 * k + 4]
-            pe = ops.PreparedBlock(w_edge, cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
-            pn = ops.PreparedBlock(w_node, cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
+            if ctx.preps is not None:
+                pe, pn = ctx.preps[k]
+            else:
+                pe = ops.PreparedBlock(w_edge, cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
+                pn = ops.PreparedBlock(w_node, cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
             # node block: g_agg, gradient of the node pre-activation, MLP weight grads
             g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale,
                                                kind="node_bwd", h0=h0n, n_nodes=plan.N)

@@ -70,6 +70,17 @@ def _worker(rank, world, port, ei, n, out):
                 ids = other.halo_global[(other.halo_global >= pl.lo) & (other.halo_global < pl.hi)] - pl.lo
                 expect[torch.from_numpy(ids)] += float(p + 1)
         ok_b = torch.equal(g_own, expect)
+        # split-phase form: post, do unrelated work, finish; receive straight into a slice of a larger buffer
+        x_ext = torch.full((pl.n_local, 4), -1.0)
+        tok = ex.forward_start(xg[pl.lo:pl.hi].contiguous(), out=x_ext[pl.n_own:])
+        x_ext[:pl.n_own] = xg[pl.lo:pl.hi]
+        ex.forward_finish(tok)
+        ok_f = ok_f and torch.equal(x_ext[pl.n_own:], xg[torch.from_numpy(pl.halo_global)])
+        g2 = torch.zeros(pl.n_own, 4)
+        tok = ex.backward_start(torch.full((pl.n_halo, 4), float(rank + 1)), g2)
+        g2 += 0.0
+        ex.backward_finish(tok, g2)
+        ok_b = ok_b and torch.equal(g2, expect)
         out[rank] = (ok_f, ok_b, pl.n_halo)
     finally:
         dist.destroy_process_group()
