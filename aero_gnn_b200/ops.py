@@ -372,6 +372,13 @@ def block_fwd(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, 
     return out, agg
 
 
+def wgrad_into(g_w: torch.Tensor, g_h0: torch.Tensor, rows_in: torch.Tensor) -> None:
+    """g_w[W_main slot] = g_h0^T rows_in, the weight gradient of a block's first Linear: a plain library GEMM over the
+    rows, written in fp32 straight into the packed gradient vector (no bf16 rounding of the result, no cast/copy
+    launches)."""
+    torch.mm(g_h0.t(), rows_in, out_dtype=torch.float32, out=g_w[: D * D].view(D, D))
+
+
 def block_bwd(prep: PreparedBlock, main, P, idx0, idx1, poff0, poff1, g_out, *, g_agg=None, main_scale=None,
               has_resid_grad=False, g_main_out: Optional[torch.Tensor] = None, kind=None,
               h0: Optional[torch.Tensor] = None, n_nodes: Optional[int] = None):

@@ -128,12 +128,12 @@ class MGNStackFn(torch.autograd.Function):
             g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale,
                                                kind="node_bwd", h0=h0n, n_nodes=plan.N)
             agg_eff = agg if scale is None else agg * scale[:, None]
-            g_wn[: D * D] = (g_h0n.t() @ agg_eff.to(dt)).float().reshape(-1)
+            ops.wgrad_into(g_wn, g_h0n, agg_eff.to(dt))
             # edge block: total gradient of e' = G_e + g_agg[receiver]
             G_e, g_h0e, g_we = ops.block_bwd(pe, e, P, plan.src, plan.dst, 0, D, G_e, g_agg=g_agg,
                                              has_resid_grad=True, g_main_out=G_e, kind="edge_bwd", h0=h0e,
                                              n_nodes=plan.N)
-            g_we[: D * D] = (g_h0e.t() @ e).float().reshape(-1)
+            ops.wgrad_into(g_we, g_h0e, e)
             # gradients of the gathered projections: segmented sums by sender and by receiver
             # (both land in one [N, 2D] matrix, so the products with W_s | W_d are single K = 2D GEMMs)
             g_psd = torch.empty((plan.N, 2 * D), dtype=dt, device=x.device)
@@ -212,7 +212,7 @@ class SingleBlockFn(torch.autograd.Function):
         P = torch.addmm(b_proj, x, w_proj.t())
         if mode == "edge":
             g_e, g_h0, g_w = ops.block_bwd(prep, e, P, plan.src, plan.dst, 0, D, g)
-            g_w[: D * D] = (g_h0.t() @ e).float().reshape(-1)
+            ops.wgrad_into(g_w, g_h0, e)
             g_ps = ops.segment_reduce(g_h0, plan.sptr, plan.sperm, plan.N)
             g_pd = ops.segment_reduce(g_h0, plan.rowptr, None, plan.N)
             g_x = torch.addmm(g_ps @ w_proj[:D], g_pd, w_proj[D:])
@@ -221,7 +221,7 @@ class SingleBlockFn(torch.autograd.Function):
         else:
             g_agg, g_h0, g_w = ops.block_bwd(prep, agg, P, None, None, 0, 0, g, main_scale=scale)
             agg_eff = agg if scale is None else agg * scale[:, None]
-            g_w[: D * D] = (g_h0.t() @ agg_eff.to(dt)).float().reshape(-1)
+            ops.wgrad_into(g_w, g_h0, agg_eff.to(dt))
             g_e = ops.gather_rows(g_agg.to(dt), plan.dst)
             g_x = g_h0 @ w_proj
             g_wproj = g_h0.t() @ x
@@ -333,7 +333,7 @@ class DenseMLPFn(torch.autograd.Function):
         x, w, P, idx0 = ctx.saved_tensors
         prep = ops.PreparedBlock(w, L, path, act, use_ln)
         g_x, g_h0, g_w = ops.block_bwd(prep, x, P, idx0, None, 0, 0, g.contiguous().to(x.dtype), kind="dense_bwd")
-        g_w[: D * D] = (g_h0.t() @ x).float().reshape(-1)          # dW_0 = g_h0^T x (library GEMM, like the processor)
+        ops.wgrad_into(g_w, g_h0, x)          # dW_0 = g_h0^T x (library GEMM, like the processor)
         return None, None, None, g_x, g_w, g_w[-D:].to(b0_dtype)   # last slot: column sums of g_h0 = d b_0
 
 
