@@ -241,3 +241,64 @@ extern "C" int aero_segment_bcast(const void* g_out, const int32_t* seg_of_row, 
   AERO_LAUNCH_CHECK();
   return AERO_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Multi-segment strided copy with dtype conversion: one launch packs all parameters of a processor step into the
+// images the block kernels read (forward) or scatters the packed gradients back into per-parameter buffers (backward).
+// ---------------------------------------------------------------------------------------------
+namespace aero {
+
+struct CopySegs {
+  aero_copy_seg s[AERO_MAX_COPY_SEGS];
+};
+
+template <typename TS, typename TD>
+__device__ __forceinline__ void copy_seg_elems(const aero_copy_seg& g) {
+  const TS* src = reinterpret_cast<const TS*>(g.src);
+  TD* dst = reinterpret_cast<TD*>(g.dst);
+  const int64_t n = g.rows * g.cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / g.cols, c = i - r * g.cols;
+    store1(dst + r * g.dst_ld + c, src ? load1(src + r * g.src_ld + c) : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256) multi_copy_kernel(const __grid_constant__ CopySegs segs) {
+  const aero_copy_seg& g = segs.s[blockIdx.y];
+  if (g.src_dtype == AERO_F32) {
+    if (g.dst_dtype == AERO_F32) copy_seg_elems<float, float>(g);
+    else copy_seg_elems<float, __nv_bfloat16>(g);
+  } else {
+    if (g.dst_dtype == AERO_F32) copy_seg_elems<__nv_bfloat16, float>(g);
+    else copy_seg_elems<__nv_bfloat16, __nv_bfloat16>(g);
+  }
+}
+
+}  // namespace aero
+
+extern "C" int aero_multi_copy(const aero_copy_seg* segs, int n_segs, void* stream) {
+  g_launch_count = 0;
+  AERO_CHECK_ARG(n_segs >= 0 && n_segs <= AERO_MAX_COPY_SEGS && (n_segs == 0 || segs),
+                 "aero_multi_copy: 0 <= n_segs <= %d", AERO_MAX_COPY_SEGS);
+  if (n_segs == 0) return AERO_OK;
+  CopySegs cs;
+  memset(&cs, 0, sizeof(cs));
+  int64_t max_elems = 1;
+  for (int i = 0; i < n_segs; ++i) {
+    const aero_copy_seg& g = segs[i];
+    AERO_CHECK_ARG(g.rows >= 0 && g.cols >= 0 && (g.rows * g.cols == 0 || g.dst) && g.src_ld >= 0 && g.dst_ld >= 0,
+                   "aero_multi_copy: bad segment %d", i);
+    if ((g.src_dtype != AERO_F32 && g.src_dtype != AERO_BF16) || (g.dst_dtype != AERO_F32 && g.dst_dtype != AERO_BF16)) {
+      set_error("aero_multi_copy: unsupported dtype in segment %d", i);
+      return AERO_EUNSUPPORTED;
+    }
+    cs.s[i] = g;
+    if (g.rows * g.cols > max_elems) max_elems = g.rows * g.cols;
+  }
+  int64_t bx = cdiv(max_elems, 256 * 4);
+  if (bx > 64) bx = 64;
+  dim3 grid((unsigned)bx, (unsigned)n_segs);
+  multi_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cs);
+  AERO_LAUNCH_CHECK();
+  return AERO_OK;
+}

@@ -49,6 +49,15 @@ class WecDesc(C.Structure):
     ]
 
 
+class CopySeg(C.Structure):
+    """Mirror of struct aero_copy_seg (include/aero_gnn.h)."""
+
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int64),
+                ("src_ld", C.c_int64), ("dst_ld", C.c_int64), ("src_dtype", C.c_int32), ("dst_dtype", C.c_int32)]
+
+
+MAX_COPY_SEGS = 48
+
 # name -> (restype, argtypes); every symbol declared in include/aero_gnn.h
 SIGNATURES = {
     "aero_last_error": (C.c_char_p, []),
@@ -88,6 +97,7 @@ SIGNATURES = {
     "aero_filter_edges_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "aero_filter_edges": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64] + [C.c_void_p] * 3
                           + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "aero_multi_copy": (C.c_int, [C.POINTER(CopySeg), C.c_int, C.c_void_p]),
     "aero_wec_workspace_bytes": (C.c_size_t, [C.POINTER(WecDesc), C.c_int]),
     "aero_wec_fwd": (C.c_int, [C.POINTER(WecDesc), C.c_void_p]),
     "aero_wec_bwd": (C.c_int, [C.POINTER(WecDesc), C.c_void_p]),

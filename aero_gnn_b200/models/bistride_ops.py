@@ -15,7 +15,7 @@ from torch import nn
 
 from .. import bistride as _b
 from .. import ops
-from ..processor import D, StackConfig, StepWeights, pack_block, permute_rows, run_stack
+from ..processor import D, StackConfig, StepWeights, pack_step, permute_rows, run_stack
 
 
 class BistridePooling:
@@ -120,11 +120,9 @@ class GMP(nn.Module):
         n0, n2, nln = self.node_mlp[0], self.node_mlp[2], self.node_mlp[3]
         w_s, w_d, w_e = e0.weight[:, :nd], e0.weight[:, nd:2 * nd], e0.weight[:, 2 * nd:]
         w_x, w_a = n0.weight[:, :nd], n0.weight[:, nd:]
-        w_edge = pack_block(w_e, [], e2.weight, e2.bias, eln.weight, eln.bias)
-        w_node = pack_block(w_a, [], n2.weight, n2.bias, nln.weight, nln.bias)
-        w_proj = torch.cat([w_s, w_d, w_x], dim=0).to(dtype)
-        b_proj = torch.cat([torch.zeros_like(e0.bias), e0.bias, n0.bias]).to(dtype)
-        return StepWeights(w_edge, w_node, w_proj, b_proj)
+        return pack_step((w_e, [], e2.weight, e2.bias, eln.weight, eln.bias),
+                         (w_a, [], n2.weight, n2.bias, nln.weight, nln.bias),
+                         [w_s, w_d, w_x], [None, e0.bias, n0.bias], dtype)
 
     def forward_csr(self, x, e_csr, plan: ops.GraphPlan):
         """The same step on edge rows already in the plan's receiver-CSR order; returns (x', e' in CSR order)."""

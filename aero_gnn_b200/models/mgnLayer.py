@@ -11,8 +11,8 @@ import torch
 from torch import nn
 
 from .. import ops
-from ..processor import (D, StackConfig, StepWeights, pack_block, run_stack, permute_rows, edge_block_apply,
-                         node_block_apply)
+from ..processor import (D, StackConfig, StepWeights, pack_block, pack_step, run_stack, permute_rows,
+                         edge_block_apply, node_block_apply)
 from .mlp import MLP
 
 
@@ -152,11 +152,9 @@ class MeshGraphNetLayer(nn.Module):
 
     def step_weights(self, dtype: torch.dtype) -> StepWeights:
         ep, np_ = self.edge_block.fused_parts(), self.node_block.fused_parts()
-        w_edge = pack_block(ep["w_e"], ep["hidden"], ep["w_out"], ep["b_out"], ep["gamma"], ep["beta"])
-        w_node = pack_block(np_["w_a"], np_["hidden"], np_["w_out"], np_["b_out"], np_["gamma"], np_["beta"])
-        w_proj = torch.cat([ep["w_s"], ep["w_d"], np_["w_x"]], dim=0).to(dtype)
-        b_proj = torch.cat([torch.zeros_like(ep["b0"]), ep["b0"], np_["b0"]]).to(dtype)
-        return StepWeights(w_edge, w_node, w_proj, b_proj)
+        return pack_step((ep["w_e"], ep["hidden"], ep["w_out"], ep["b_out"], ep["gamma"], ep["beta"]),
+                         (np_["w_a"], np_["hidden"], np_["w_out"], np_["b_out"], np_["gamma"], np_["beta"]),
+                         [ep["w_s"], ep["w_d"], np_["w_x"]], [None, ep["b0"], np_["b0"]], dtype)
 
     def forward(self, node_attr, edge_attr, edge_index):
         ops._require_cuda(node_attr, edge_attr, edge_index)

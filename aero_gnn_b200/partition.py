@@ -225,7 +225,9 @@ class PartitionedStackFn(torch.autograd.Function):
             tok = ex.backward_start(g_ext[n_own:], g_ext)           # halo-row gradients travel under the GEMMs below
             g_x = G_x + g_ext[:n_own]
             g_x.addmm_(g_h0n, w_proj[2 * D:])
-            g_wproj = torch.cat([g_psd.t() @ x_ext, g_h0n.t() @ x], dim=0)
+            g_wproj = torch.empty_like(w_proj)
+            torch.mm(g_psd.t(), x_ext, out=g_wproj[:2 * D])
+            torch.mm(g_h0n.t(), x, out=g_wproj[2 * D:])
             g_bproj = torch.cat([g_we[-D:], g_we[-D:], g_wn[-D:]])
             ex.backward_finish(tok, g_x)
             grads[4 * k: 4 * k + 4] = [g_we, g_wn, g_wproj.to(w_proj.dtype), g_bproj.to(b_proj.dtype)]

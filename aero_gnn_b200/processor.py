@@ -56,6 +56,144 @@ def pack_block(w_main, hidden: Sequence, w_out, b_out, gamma, beta) -> torch.Ten
     return torch.cat([p.float() for p in parts])
 
 
+# ------------------------------------------------------------------------------------------------
+# one-launch packing of a step's parameters (and one-launch scatter of their gradients)
+# ------------------------------------------------------------------------------------------------
+def _locate(t: torch.Tensor):
+    """(base tensor, element offset inside it, rows, cols, row stride) of a parameter or of a column-slice view of
+    one (e.g. W0[:, :128]); the base is what autograd sees, so no Slice/Cat backward nodes are created."""
+    base = t._base if t._base is not None else t
+    if t.dim() == 2:
+        rows, cols, ld = t.size(0), t.size(1), t.stride(0)
+        ok = t.stride(1) == 1
+    else:
+        rows, cols, ld = 1, t.numel(), t.numel()
+        ok = t.dim() == 1 and (t.numel() <= 1 or t.stride(0) == 1)
+    if not (ok and base.is_contiguous()):
+        raise RuntimeError("pack_step: parameters must be contiguous (column slices of a contiguous matrix are fine)")
+    return base, t.storage_offset() - base.storage_offset(), rows, cols, ld
+
+
+class PackSpec:
+    """Where every parameter piece of a step goes: outs = [(numel, dtype)], segs = [(base index | None, element offset in
+    the base, rows, cols, base row stride, out index, element offset in the out, out row stride)]."""
+
+    def __init__(self):
+        self.bases, self.outs, self.segs = [], [], []
+
+    def out(self, numel: int, dtype) -> int:
+        self.outs.append((int(numel), dtype))
+        return len(self.outs) - 1
+
+    def put(self, t: Optional[torch.Tensor], out: int, off: int, rows: int = 1, cols: int = D, out_ld: Optional[int] = None):
+        if t is None:                                   # zero fill
+            self.segs.append((None, 0, rows, cols, cols, out, off, out_ld or cols))
+            return
+        base, boff, r, c, ld = _locate(t)
+        if r * c != rows * cols:
+            raise RuntimeError(f"pack_step: a parameter piece has {r}x{c} elements, expected {rows}x{cols}")
+        for i, b in enumerate(self.bases):
+            if b is base:
+                break
+        else:
+            self.bases.append(base)
+            i = len(self.bases) - 1
+        self.segs.append((i, boff, r, c, ld, out, off, out_ld or c))
+
+
+def _multi_copy(segs) -> None:
+    lib = ops._l.load()
+    for i in range(0, len(segs), ops._l.MAX_COPY_SEGS):
+        chunk = segs[i: i + ops._l.MAX_COPY_SEGS]
+        arr = (ops._l.CopySeg * len(chunk))(*chunk)
+        rc = lib.aero_multi_copy(arr, len(chunk), ops._stream())
+        ops._l.check(rc, "aero_multi_copy")
+        ops.LaunchCounter.add()
+
+
+class PackStepFn(torch.autograd.Function):
+    """apply(spec, *spec.bases) -> one tensor per spec.outs entry, filled by ONE kernel launch; the backward scatters
+    the gradients of those tensors into one gradient buffer per base with ONE launch (replaces the torch.cat /
+    dtype-cast / slice chains and their autograd nodes, ~15 small launches per processor step)."""
+
+    @staticmethod
+    def forward(ctx, spec: PackSpec, *bases):
+        dev = bases[0].device
+        ops._require_cuda(*bases)
+        outs = [torch.empty(n, dtype=dt, device=dev) for n, dt in spec.outs]
+        segs = []
+        for bi, boff, r, c, ld, oi, ooff, old in spec.segs:
+            o = outs[oi]
+            src = None if bi is None else bases[bi].data_ptr() + boff * bases[bi].element_size()
+            segs.append(ops._l.CopySeg(src, o.data_ptr() + ooff * o.element_size(), r, c, ld, old,
+                                       ops.dtype_code(bases[bi]) if bi is not None else ops.dtype_code(o),
+                                       ops.dtype_code(o)))
+        with torch.cuda.device(dev):
+            _multi_copy(segs)
+        ctx.spec = spec
+        ctx.meta = [(b.shape, b.dtype) for b in bases]
+        ctx.dev = dev
+        ctx.set_materialize_grads(False)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        spec, dev = ctx.spec, ctx.dev
+        gouts = [None if g is None else g.contiguous() for g in gouts]
+        covered = [0] * len(ctx.meta)
+        for bi, _, r, c, *_rest in spec.segs:
+            if bi is not None:
+                covered[bi] += r * c
+        grads = []
+        for i, (shape, dt) in enumerate(ctx.meta):
+            if not ctx.needs_input_grad[1 + i]:
+                grads.append(None)
+                continue
+            full = covered[i] == int(torch.Size(shape).numel())
+            grads.append((torch.empty if full else torch.zeros)(shape, dtype=dt, device=dev))
+        segs = []
+        for bi, boff, r, c, ld, oi, ooff, old in spec.segs:
+            if bi is None or grads[bi] is None:
+                continue
+            g, go = grads[bi], gouts[oi]
+            src = None if go is None else go.data_ptr() + ooff * go.element_size()
+            segs.append(ops._l.CopySeg(src, g.data_ptr() + boff * g.element_size(), r, c, old, ld,
+                                       ops.dtype_code(go) if go is not None else ops.dtype_code(g), ops.dtype_code(g)))
+        with torch.cuda.device(dev):
+            _multi_copy(segs)
+        return (None, *grads)
+
+
+def pack_step(edge, node, proj_w: Sequence, proj_b: Sequence, dtype: torch.dtype) -> StepWeights:
+    """StepWeights of one processor step from the reference-named parameters.  `edge` / `node` =
+    (w_main, hidden [(W, b)...], w_out, b_out, gamma, beta); proj_w = the [D, D] blocks of the node pre-projection
+    (sender part, receiver part, node-block part); proj_b = their biases (None = zeros)."""
+    spec = PackSpec()
+    outs = []
+    for (w_main, hidden, w_out, b_out, gamma, beta) in (edge, node):
+        L = len(hidden)
+        o = spec.out(ops.packed_floats(L), torch.float32)
+        outs.append(o)
+        spec.put(w_main, o, 0, D, D)
+        for l, (w, _) in enumerate(hidden):
+            spec.put(w, o, (1 + l) * D * D, D, D)
+        spec.put(w_out, o, (1 + L) * D * D, D, D)
+        voff = (2 + L) * D * D
+        for l, (_, b) in enumerate(hidden):
+            spec.put(b, o, voff + l * D)
+        spec.put(b_out, o, voff + L * D)
+        spec.put(gamma, o, voff + (L + 1) * D)
+        spec.put(beta, o, voff + (L + 2) * D)
+        spec.put(None, o, voff + (L + 3) * D)            # gradient-only slot of the first Linear's bias
+    k = len(proj_w)
+    ow, ob = spec.out(k * D * D, dtype), spec.out(k * D, dtype)
+    for i, (w, b) in enumerate(zip(proj_w, proj_b)):
+        spec.put(w, ow, i * D * D, D, D)
+        spec.put(b, ob, i * D)
+    w_edge, w_node, w_proj, b_proj = PackStepFn.apply(spec, *spec.bases)
+    return StepWeights(w_edge, w_node, w_proj.view(k * D, D), b_proj)
+
+
 class MGNStackFn(torch.autograd.Function):
     """apply(cfg, plan, x, e_csr, *flat) with flat = (w_edge, w_node, w_proj, b_proj) per step."""
 
@@ -141,7 +279,9 @@ class MGNStackFn(torch.autograd.Function):
             ops.segment_reduce(g_h0e, plan.rowptr, None, plan.N, out=g_psd[:, D:])
             g_x = torch.addmm(G_x, g_psd, w_proj[:2 * D])
             g_x.addmm_(g_h0n, w_proj[2 * D:])
-            g_wproj = torch.cat([g_psd.t() @ x, g_h0n.t() @ x], dim=0)
+            g_wproj = torch.empty_like(w_proj)
+            torch.mm(g_psd.t(), x, out=g_wproj[:2 * D])
+            torch.mm(g_h0n.t(), x, out=g_wproj[2 * D:])
             # column sums of g_h0 come out of the block kernels (fp32): sum over edges == sum over senders == receivers
             g_bproj = torch.cat([g_we[-D:], g_we[-D:], g_wn[-D:]])
             grads[4 * k: 4 * k + 4] = [g_we, g_wn, g_wproj.to(w_proj.dtype), g_bproj.to(b_proj.dtype)]

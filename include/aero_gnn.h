@@ -130,6 +130,20 @@ int aero_segment_reduce_ld(const void* in, const int32_t* ptr, const int32_t* li
 int aero_segment_bcast(const void* g_out, const int32_t* seg_of_row, const int32_t* ptr,
                        void* g_in, int64_t n_rows, int64_t width, int dtype, int mean, void* stream);
 
+/* Several strided 2-D copies with dtype conversion in ONE launch: packs the reference-named parameters of a processor
+ * step (mgnLayer.py:26-30,68-91,124-132 -> nn.Linear / LayerNorm tensors) into the packed vectors below, and scatters
+ * the packed gradients back into per-parameter buffers.  src == NULL fills the destination with zeros.  `segs` is a
+ * HOST array (copied into the kernel's parameter space). */
+#define AERO_MAX_COPY_SEGS 48
+typedef struct aero_copy_seg {
+  const void* src;
+  void* dst;
+  int64_t rows, cols;       /* `cols` contiguous elements per row                     */
+  int64_t src_ld, dst_ld;   /* elements between consecutive rows                      */
+  int32_t src_dtype, dst_dtype;   /* AERO_F32 | AERO_BF16                              */
+} aero_copy_seg;
+int aero_multi_copy(const aero_copy_seg* segs, int n_segs, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused MGN block (edge block or node block of one processor step).
  *

@@ -92,20 +92,69 @@ def test_mlp_module_matches_oracle():
     assert len(single.layers) == 1 and single.layers[0].weight.shape == (3, 5)
 
 
-def test_packed_weight_layout():
+def _emulate_pack(spec, bases):
+    """What aero_multi_copy does with a PackSpec, on CPU tensors (test-side emulation of the segment list)."""
+    outs = [torch.full((n,), float("nan"), dtype=torch.float32) for n, _ in spec.outs]
+    for bi, boff, r, c, ld, oi, ooff, old in spec.segs:
+        for i in range(r):
+            row = torch.zeros(c) if bi is None else bases[bi].detach().reshape(-1)[boff + i * ld: boff + i * ld + c].float()
+            outs[oi][ooff + i * old: ooff + i * old + c] = row
+    return outs
+
+
+def test_packed_weight_layout(monkeypatch):
+    """The segment list of the one-launch parameter packing (processor.pack_step) reproduces the packed layout of
+    include/aero_gnn.h for both edge-block forms; every parameter element is used exactly once."""
     import aero_gnn_b200.models as M
+    from aero_gnn_b200 import processor as P
     from aero_gnn_b200.ops import packed_floats
+    seen = {}
+
+    class _Stop(Exception):
+        pass
+
+    def fake_apply(spec, *bases):
+        seen["spec"], seen["bases"] = spec, bases
+        raise _Stop
+
+    monkeypatch.setattr(P.PackStepFn, "apply", staticmethod(fake_apply))
+
+    def spec_of(layer):
+        with pytest.raises(_Stop):
+            layer.step_weights(torch.float32)
+        spec, bases = seen["spec"], seen["bases"]
+        used = [0] * len(bases)
+        for bi, _, r, c, *_rest in spec.segs:
+            if bi is not None:
+                used[bi] += r * c
+        assert used == [b.numel() for b in bases]
+        assert {id(b) for b in bases} == {id(p) for p in layer.parameters()}
+        return _emulate_pack(spec, bases)
+
     layer = M.MeshGraphNetLayer(128, 128, 128, 2, 2, do_concat_trick=True)
-    sw = layer.step_weights(torch.float32)
-    assert sw.w_edge.numel() == packed_floats(2) and sw.w_node.numel() == packed_floats(2)
-    assert sw.w_proj.shape == (384, 128) and sw.b_proj.shape == (384,)
-    assert torch.equal(sw.w_edge[:16384].view(128, 128), layer.edge_block.edge_lin.detach())
-    assert torch.equal(sw.w_proj[256:], layer.node_block.mlp.layers[0].weight[:, :128].detach())
-    assert torch.equal(sw.w_node[:16384].view(128, 128), layer.node_block.mlp.layers[0].weight[:, 128:].detach())
+    w_edge, w_node, w_proj, b_proj = spec_of(layer)
+    assert w_edge.numel() == packed_floats(2) and w_node.numel() == packed_floats(2)
+    assert not torch.isnan(torch.cat([w_edge, w_node, w_proj, b_proj])).any()
+    w_proj = w_proj.view(384, 128)
+    assert b_proj.shape == (384,) and torch.equal(b_proj[:128], torch.zeros(128))
+    assert torch.equal(w_edge[:16384].view(128, 128), layer.edge_block.edge_lin.detach())
+    assert torch.equal(w_proj[256:], layer.node_block.mlp.layers[0].weight[:, :128].detach())
+    assert torch.equal(w_node[:16384].view(128, 128), layer.node_block.mlp.layers[0].weight[:, 128:].detach())
+    # against the torch-op packing the single-block paths still use
+    ep = layer.edge_block.fused_parts()
+    ref = P.pack_block(ep["w_e"], ep["hidden"], ep["w_out"], ep["b_out"], ep["gamma"], ep["beta"]).detach()
+    assert torch.equal(w_edge, ref)
+    assert torch.equal(b_proj[128:256], layer.edge_block.bias.detach())
     cat = M.MeshGraphNetLayer(128, 128, 128, 1, 1, do_concat_trick=False)
-    sw2 = cat.step_weights(torch.float32)
+    w_edge2, _, w_proj2, _ = spec_of(cat)
     w0 = cat.edge_block.mlp.layers[0].weight.detach()
-    assert torch.equal(sw2.w_edge[:16384].view(128, 128), w0[:, :128]) and torch.equal(sw2.w_proj[:128], w0[:, 128:256])
+    assert torch.equal(w_edge2[:16384].view(128, 128), w0[:, :128])
+    assert torch.equal(w_proj2.view(384, 128)[:128], w0[:, 128:256])
+    gmp = M.GMP(128, 128, 128)
+    w_edge3, w_node3, w_proj3, b_proj3 = spec_of(gmp)
+    e0 = gmp.edge_mlp[0].weight.detach()      # [x_src | x_dst | e]
+    assert torch.equal(w_edge3[:16384].view(128, 128), e0[:, 256:]) and torch.equal(w_proj3.view(384, 128)[:128], e0[:, :128])
+    assert w_edge3.numel() == packed_floats(0)
 
 
 def test_synthetic_meshes():

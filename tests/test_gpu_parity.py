@@ -457,3 +457,42 @@ def test_mlp_fused_decoder_fp32_vs_chain(rows, out_dim, nh, ln):
     assert rel_err(out, h) < 1e-5, rel_err(out, h)
     for a, b in zip(got, want):
         assert rel_err(a, b) < 1e-4, rel_err(a, b)
+
+
+# ---- one-launch parameter packing (aero_multi_copy) vs the torch-op packing and its autograd ----------------------
+@pytest.mark.parametrize("concat,L,dtype", [(True, 2, torch.bfloat16), (False, 1, torch.float32), (True, 0, torch.float32)])
+def test_pack_step_matches_torch_packing_and_routes_gradients(concat, L, dtype):
+    from aero_gnn_b200 import processor as P
+    M = _mods()
+    torch.manual_seed(L)
+    if L == 0:
+        layer = M.GMP(128, 128, 128).to(DEV).to(dtype)
+        nd = 128
+        e0, e2, eln = layer.edge_mlp[0], layer.edge_mlp[2], layer.edge_mlp[3]
+        n0, n2, nln = layer.node_mlp[0], layer.node_mlp[2], layer.node_mlp[3]
+        parts = lambda: ((e0.weight[:, 2 * nd:], [], e2.weight, e2.bias, eln.weight, eln.bias),
+                         (n0.weight[:, nd:], [], n2.weight, n2.bias, nln.weight, nln.bias),
+                         [e0.weight[:, :nd], e0.weight[:, nd:2 * nd], n0.weight[:, :nd]], [None, e0.bias, n0.bias])
+    else:
+        layer = M.MeshGraphNetLayer(128, 128, 128, L, L, do_concat_trick=concat).to(DEV).to(dtype)
+
+        def parts():
+            ep, np_ = layer.edge_block.fused_parts(), layer.node_block.fused_parts()
+            return ((ep["w_e"], ep["hidden"], ep["w_out"], ep["b_out"], ep["gamma"], ep["beta"]),
+                    (np_["w_a"], np_["hidden"], np_["w_out"], np_["b_out"], np_["gamma"], np_["beta"]),
+                    [ep["w_s"], ep["w_d"], np_["w_x"]], [None, ep["b0"], np_["b0"]])
+    sw = layer.step_weights(dtype)
+    edge, node, pw, pb = parts()
+    ref = [P.pack_block(*edge), P.pack_block(*node), torch.cat(pw, dim=0).to(dtype),
+           torch.cat([torch.zeros_like(pb[1]), pb[1], pb[2]]).to(dtype)]
+    got = [sw.w_edge, sw.w_node, sw.w_proj, sw.b_proj]
+    for a, b in zip(got, ref):
+        assert a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b)
+    g = torch.Generator().manual_seed(3)
+    gs = [torch.randn(t.shape, generator=g).to(DEV, t.dtype) for t in got]
+    torch.autograd.backward(got, gs)
+    mine = {k: p.grad.clone() for k, p in layer.named_parameters()}
+    layer.zero_grad(set_to_none=True)
+    torch.autograd.backward(ref, gs)
+    for k, p in layer.named_parameters():
+        assert mine[k].dtype == p.grad.dtype and torch.equal(mine[k], p.grad), k
