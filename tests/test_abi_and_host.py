@@ -168,3 +168,27 @@ def test_synthetic_meshes():
     assert torch.unique(m.pos[:, 0]).numel() == m.num_nodes          # no x ties
     b = batch_meshes([airfoil_o_mesh(10, 5, seed=s) for s in range(3)])
     assert b.num_nodes == 150 and int(b.batch.max()) == 2
+
+
+def test_pack_spec_rejects_what_the_copy_kernel_cannot_address():
+    """processor._locate / PackSpec: column slices of contiguous matrices are fine, transposed or strided pieces and
+    wrongly sized pieces are refused before anything is launched."""
+    from aero_gnn_b200 import processor as P
+    w = torch.nn.Parameter(torch.randn(128, 384))
+    base, off, r, c, ld = P._locate(w[:, 128:256])
+    assert base is w and (off, r, c, ld) == (128, 128, 128, 384)
+    b = torch.nn.Parameter(torch.randn(128))
+    assert P._locate(b)[1:] == (0, 1, 128, 128)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        P._locate(w.t()[:128])
+    with pytest.raises(RuntimeError, match="contiguous"):
+        P._locate(w[:, ::2])
+    spec = P.PackSpec()
+    o = spec.out(128 * 128, torch.float32)
+    spec.put(w[:, :128], o, 0, 128, 128)
+    spec.put(w[:, 128:256], o, 0, 128, 128)
+    assert len(spec.bases) == 1 and [s[1] for s in spec.segs] == [0, 128]      # one autograd input, two pieces
+    with pytest.raises(RuntimeError, match="expected"):
+        spec.put(b, o, 0, 128, 128)
+    spec.put(None, o, 0)                                                          # zero fill: no base
+    assert spec.segs[-1][0] is None
