@@ -13,7 +13,7 @@ from __future__ import annotations
 import ctypes as C
 from collections import OrderedDict
 from dataclasses import dataclass
-from typing import List, Optional
+from typing import Optional
 
 import torch
 

@@ -17,7 +17,7 @@ from torch import nn
 from .. import bistride as _b
 from .. import ops
 from ..processor import permute_rows
-from .bistride_ops import GMP, BistridePooling, Unpool, WeightedEdgeConv, _index_maps
+from .bistride_ops import GMP, Unpool, WeightedEdgeConv, _index_maps
 from .mlp import MLP
 
 

@@ -11,8 +11,8 @@ import torch
 from torch import nn
 
 from .. import ops
-from ..processor import (D, StackConfig, StepWeights, pack_block, pack_step, run_stack, permute_rows,
-                         edge_block_apply, node_block_apply)
+from ..processor import (D, StackConfig, StepWeights, pack_step, run_stack, permute_rows, edge_block_apply,
+                         node_block_apply)
 from .mlp import MLP
 
 
