@@ -15,7 +15,7 @@ from torch import nn
 
 from .. import bistride as _b
 from .. import ops
-from ..processor import D, StackConfig, StepWeights, pack_step, permute_rows, run_stack
+from ..processor import D, StackConfig, StepWeights, cached_pack_step, permute_rows, run_stack
 
 
 class BistridePooling:
@@ -115,14 +115,16 @@ class GMP(nn.Module):
         return StackConfig(L_edge=0, L_node=0, act_edge="relu", act_node="relu", use_ln=True, mean=False)
 
     def step_weights(self, dtype: torch.dtype) -> StepWeights:
-        nd, ed, _ = self.dims
-        e0, e2, eln = self.edge_mlp[0], self.edge_mlp[2], self.edge_mlp[3]
-        n0, n2, nln = self.node_mlp[0], self.node_mlp[2], self.node_mlp[3]
-        w_s, w_d, w_e = e0.weight[:, :nd], e0.weight[:, nd:2 * nd], e0.weight[:, 2 * nd:]
-        w_x, w_a = n0.weight[:, :nd], n0.weight[:, nd:]
-        return pack_step((w_e, [], e2.weight, e2.bias, eln.weight, eln.bias),
-                         (w_a, [], n2.weight, n2.bias, nln.weight, nln.bias),
-                         [w_s, w_d, w_x], [None, e0.bias, n0.bias], dtype)
+        def build():
+            nd = self.dims[0]
+            e0, e2, eln = self.edge_mlp[0], self.edge_mlp[2], self.edge_mlp[3]
+            n0, n2, nln = self.node_mlp[0], self.node_mlp[2], self.node_mlp[3]
+            w_s, w_d, w_e = e0.weight[:, :nd], e0.weight[:, nd:2 * nd], e0.weight[:, 2 * nd:]
+            w_x, w_a = n0.weight[:, :nd], n0.weight[:, nd:]
+            return ((w_e, [], e2.weight, e2.bias, eln.weight, eln.bias),
+                    (w_a, [], n2.weight, n2.bias, nln.weight, nln.bias),
+                    [w_s, w_d, w_x], [None, e0.bias, n0.bias])
+        return cached_pack_step(self, dtype, build)
 
     def forward_csr(self, x, e_csr, plan: ops.GraphPlan):
         """The same step on edge rows already in the plan's receiver-CSR order; returns (x', e' in CSR order)."""

@@ -11,7 +11,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from ..processor import (D, StackConfig, StepWeights, pack_step, run_stack, permute_rows, edge_block_apply,
+from ..processor import (D, StackConfig, StepWeights, cached_pack_step, run_stack, permute_rows, edge_block_apply,
                          node_block_apply)
 from .mlp import MLP
 
@@ -151,10 +151,12 @@ class MeshGraphNetLayer(nn.Module):
                            act_node=np_["act"], use_ln=ep["use_ln"], mean=self.node_block.check_aggregation())
 
     def step_weights(self, dtype: torch.dtype) -> StepWeights:
-        ep, np_ = self.edge_block.fused_parts(), self.node_block.fused_parts()
-        return pack_step((ep["w_e"], ep["hidden"], ep["w_out"], ep["b_out"], ep["gamma"], ep["beta"]),
-                         (np_["w_a"], np_["hidden"], np_["w_out"], np_["b_out"], np_["gamma"], np_["beta"]),
-                         [ep["w_s"], ep["w_d"], np_["w_x"]], [None, ep["b0"], np_["b0"]], dtype)
+        def build():
+            ep, np_ = self.edge_block.fused_parts(), self.node_block.fused_parts()
+            return ((ep["w_e"], ep["hidden"], ep["w_out"], ep["b_out"], ep["gamma"], ep["beta"]),
+                    (np_["w_a"], np_["hidden"], np_["w_out"], np_["b_out"], np_["gamma"], np_["beta"]),
+                    [ep["w_s"], ep["w_d"], np_["w_x"]], [None, ep["b0"], np_["b0"]])
+        return cached_pack_step(self, dtype, build)
 
     def forward(self, node_attr, edge_attr, edge_index):
         ops._require_cuda(node_attr, edge_attr, edge_index)

@@ -164,8 +164,8 @@ class PackStepFn(torch.autograd.Function):
         return (None, *grads)
 
 
-def pack_step(edge, node, proj_w: Sequence, proj_b: Sequence, dtype: torch.dtype) -> StepWeights:
-    """StepWeights of one processor step from the reference-named parameters.  `edge` / `node` =
+def pack_step_spec(edge, node, proj_w: Sequence, proj_b: Sequence, dtype: torch.dtype) -> PackSpec:
+    """Segment list that packs one processor step from the reference-named parameters.  `edge` / `node` =
     (w_main, hidden [(W, b)...], w_out, b_out, gamma, beta); proj_w = the [D, D] blocks of the node pre-projection
     (sender part, receiver part, node-block part); proj_b = their biases (None = zeros)."""
     spec = PackSpec()
@@ -190,8 +190,33 @@ def pack_step(edge, node, proj_w: Sequence, proj_b: Sequence, dtype: torch.dtype
     for i, (w, b) in enumerate(zip(proj_w, proj_b)):
         spec.put(w, ow, i * D * D, D, D)
         spec.put(b, ob, i * D)
+    spec.dtype = dtype
+    return spec
+
+
+def apply_pack_spec(spec: PackSpec) -> StepWeights:
     w_edge, w_node, w_proj, b_proj = PackStepFn.apply(spec, *spec.bases)
-    return StepWeights(w_edge, w_node, w_proj.view(k * D, D), b_proj)
+    return StepWeights(w_edge, w_node, w_proj.view(-1, D), b_proj)
+
+
+def pack_step(edge, node, proj_w: Sequence, proj_b: Sequence, dtype: torch.dtype) -> StepWeights:
+    return apply_pack_spec(pack_step_spec(edge, node, proj_w, proj_b, dtype))
+
+
+def cached_pack_step(module: torch.nn.Module, dtype: torch.dtype, build) -> StepWeights:
+    """pack_step with the segment list remembered on `module`: it depends only on which Parameter objects the module
+    holds and on their layout, not on their values or addresses (those are read at launch), so the per-step host work
+    is one comparison of the parameter list instead of ~25 view constructions.  `build()` -> the pack_step arguments."""
+    params = tuple(module.parameters())
+    hit = module.__dict__.get("_aero_pack_cache")
+    if hit is not None:
+        key, spec = hit
+        if spec.dtype == dtype and len(key) == len(params) and all(
+                a is b and sh == b.shape and dt == b.dtype and dv == b.device for (a, sh, dt, dv), b in zip(key, params)):
+            return apply_pack_spec(spec)
+    spec = pack_step_spec(*build(), dtype)
+    module.__dict__["_aero_pack_cache"] = (tuple((p, p.shape, p.dtype, p.device) for p in params), spec)
+    return apply_pack_spec(spec)
 
 
 class MGNStackFn(torch.autograd.Function):

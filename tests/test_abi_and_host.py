@@ -192,3 +192,30 @@ def test_pack_spec_rejects_what_the_copy_kernel_cannot_address():
         spec.put(b, o, 0, 128, 128)
     spec.put(None, o, 0)                                                          # zero fill: no base
     assert spec.segs[-1][0] is None
+
+
+def test_pack_spec_is_cached_per_module_and_invalidated(monkeypatch):
+    import aero_gnn_b200.models as M
+    from aero_gnn_b200 import processor as P
+    seen = []
+    monkeypatch.setattr(P.PackStepFn, "apply", staticmethod(lambda spec, *bases: (seen.append(spec), [torch.zeros(128)] * 4)[1]))
+    layer = M.MeshGraphNetLayer(128, 128, 128, 2, 2, do_concat_trick=True)
+    layer.step_weights(torch.float32)
+    layer.step_weights(torch.float32)
+    assert seen[0] is seen[1]                                  # same segment list, no views rebuilt
+    with torch.no_grad():
+        layer.edge_block.bias.add_(1.0)                        # values are read at launch: still valid
+    layer.step_weights(torch.float32)
+    assert seen[2] is seen[0]
+    layer.step_weights(torch.bfloat16)                         # other latent dtype: other outputs
+    assert seen[3] is not seen[0]
+    layer.edge_block.bias = torch.nn.Parameter(torch.zeros(128))   # a replaced Parameter object
+    layer.step_weights(torch.bfloat16)
+    assert seen[4] is not seen[3] and any(b is layer.edge_block.bias for b in seen[4].bases)
+    layer.to(torch.float64)                                    # same objects, new dtype
+    layer.step_weights(torch.bfloat16)
+    assert seen[5] is not seen[4]
+    import copy
+    twin = copy.deepcopy(layer)
+    twin.step_weights(torch.bfloat16)
+    assert all(any(b is p for p in twin.parameters()) for b in seen[6].bases)
