@@ -5,7 +5,7 @@ Parameter names are the checkpoint contract: `layers.{i}.weight|bias` and `layer
 block kernels (processor.py reads the parameters through `split_first` / `tail`); called on its own
 (encoders) everything after its first Linear runs on the same fused block kernel (processor.DenseTailFn); a
 128-wide input (the decoder) runs whole on it, a narrower last Linear zero-padded (processor.DenseMLPFn); shapes
-the kernel does not cover stay a dense row-wise chain of library ops.
+the kernel does not cover stay a dense row-wise chain of library ops on the GPU.  CPU tensors are refused.
 """
 from __future__ import annotations
 
@@ -50,6 +50,8 @@ class MLP(nn.Module):
         return out == D or (out < D and not self.use_layer_norm and self.layers[0].in_features == D)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        from ..ops import _require_cuda
+        _require_cuda(x)                                   # like every module of the path: no CPU fallback
         if self._fusable(x):
             from ..ops import D
             from ..processor import dense_mlp, dense_tail

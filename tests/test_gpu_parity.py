@@ -496,3 +496,15 @@ def test_pack_step_matches_torch_packing_and_routes_gradients(concat, L, dtype):
     torch.autograd.backward(ref, gs)
     for k, p in layer.named_parameters():
         assert mine[k].dtype == p.grad.dtype and torch.equal(mine[k], p.grad), k
+
+
+def test_mlp_module_vs_golden_on_gpu():
+    """models/mlp.py:40-51 with widths the fused kernel does not cover (7 -> 32 -> 32 -> 16): the library chain on the
+    GPU against the output recorded from the reference."""
+    M = _mods()
+    g = load_golden("mlp")
+    m = M.MLP(7, 32, 16, 2, "relu")
+    m.load_state_dict(g["state"], strict=True)
+    m = m.to(DEV)
+    assert not m._fusable(g["x"].to(DEV))
+    assert rel_err(m(g["x"].to(DEV)), g["out"]) < TOL
