@@ -3,7 +3,8 @@
 PARITY UNPINNED: upstream ships these components only as CPython 3.11 bytecode
 (/root/reference/models/__pycache__/bistride_ops.cpython-311.pyc and the stale bsms_mgn.cpython-311.pyc); there is no
 source, no test, no golden vector, and the bytecode cannot execute on this image's Python 3.12.  The functions below
-restate the behaviour decoded from the marshal stream (oracle/decode_bistride_pyc.py prints the
+restate the behaviour decoded from the marshal stream (oracle/decode_bistride_pyc.py prints --
+and oracle/bistride_pyc_decoded.txt holds, for readers without the reference checkout -- the
 constants, names and load order the restatement was checked against: hidden width 64, fallback ratio 0.3, the
 cat orders [x_src, x_dst, len] / [x_src, x_dst, e] / [x, agg], pos[dst] - pos[src], `a = a + b` residuals).
 "orig :NN" = first line of the code object in the pyc.  Plain torch CPU tensors, Python loops for the BFS.
