@@ -114,7 +114,7 @@ class BSMS_MeshGraphNet(nn.Module):
     def forward(self, node_attr, edge_attr, edge_index, multi_data=None):
         ops._require_cuda(node_attr, edge_attr, edge_index)
         if multi_data is None:
-            raise ValueError("multi_data must be provided. Use MultiScaleGraphPreprocessor to create it.")
+            raise ValueError("multi_data must be provided. Use MultiScaleGraphPreprocessor to preprocess graphs before training.")
         node_hidden = self.node_encoder(node_attr)
         # raw edge features go into receiver-CSR order once, before the encoder (a few columns per edge instead of a
         # 128-wide latent row per GMP call); coarse-level edge latents start as zeros, which any order leaves unchanged

@@ -454,3 +454,76 @@ def test_c3_bsms_gmp_model_at_100k_nodes():
     assert torch.allclose(o1.double().sum(0), (x.double() * outdeg[:, None]).sum(0), rtol=1e-6, atol=1e-2)
     o2, _ = conv(x, data.edge_index, data.pos, edge_weights=ones, compute_weights=False)
     assert torch.equal(o1, o2)                                                      # deterministic
+
+
+# ------------------------------------------------------------------------------------------------
+# the CUDA path against vectors recorded by executing the reference's own bytecode (tests/golden/bistride.pt,
+# oracle/gen_bistride_golden.py + oracle/pyc311_vm.py)
+# ------------------------------------------------------------------------------------------------
+def test_cuda_path_vs_reference_bytecode_golden():
+    from conftest import load_golden
+    M = _M()
+    G = load_golden("bistride")
+    mesh = G["mesh"]
+    for r in G["bfs"]:
+        assert torch.equal(M.BistridePooling.bfs_distance(r["edge_index"].to(DEV), r["n"], r["start"]).cpu(), r["dist"])
+    for r in G["select"]:
+        got = M.BistridePooling.select_bistride_nodes(r["edge_index"].to(DEV), r["n"],
+                                                      None if r["pos"] is None else r["pos"].to(DEV))
+        assert torch.equal(got.cpu(), r["selected"])
+    u = G["unpool"]
+    assert torch.equal(M.Unpool()(u["x"].to(DEV), u["indices"].to(DEV), u["n"]).cpu(), u["out"])
+    data = types.SimpleNamespace(edge_index=mesh["edge_index"].to(DEV), pos=mesh["pos"].to(DEV))
+    for levels in (1, 3):
+        ref = G[f"model_L{levels}"]["multi"]
+        got = M.MultiScaleGraphPreprocessor(levels).create_multiscale_graph(data)
+        assert got["num_nodes"] == [int(v) for v in ref["num_nodes"]]
+        for key in ("node_indices", "edge_indices", "positions"):
+            for a, b in zip(got[key], ref[key]):
+                assert torch.equal(a.cpu(), b), key
+    # WeightedEdgeConv: computed weights (add / mean) and reused weights, with gradients
+    for r in G["wec"]:
+        torch.manual_seed(r["seed"])
+        conv = M.WeightedEdgeConv(128, 128, aggr=r["aggr"]).to(DEV)
+        x = r["x"].to(DEV).requires_grad_(True)
+        out, w = conv(x, r["edge_index"].to(DEV), r["pos"].to(DEV))
+        assert rel_err(out, r["out"]) < TOL and rel_err(w, r["w"]) < TOL
+        torch.autograd.backward([out, w], [r["g_out"].to(DEV), r["g_w"].to(DEV)])
+        assert rel_l2(x.grad, r["g_x"]) < 2e-3 and _rows_off(x.grad, r["g_x"]) <= 4
+        for k, p in conv.named_parameters():
+            assert rel_l2(p.grad, r["g_params"][k]) < 2e-3, k
+        conv.zero_grad(set_to_none=True)
+        x2, ew = r["x"].to(DEV).requires_grad_(True), r["ew"].to(DEV).requires_grad_(True)
+        out2, _ = conv(x2, r["edge_index"].to(DEV), r["pos"].to(DEV), edge_weights=ew, compute_weights=False)
+        assert rel_err(out2, r["out_reuse"]) < TOL
+        out2.backward(r["g_out"].to(DEV))
+        assert rel_err(x2.grad, r["g_x_reuse"]) < GTOL and rel_err(ew.grad, r["g_ew"]) < GTOL
+    # GMP on the random multigraph
+    r = G["gmp"]
+    torch.manual_seed(r["seed"])
+    gmp = M.GMP(128, 128, 128).to(DEV)
+    x, e = r["x"].to(DEV).requires_grad_(True), r["e"].to(DEV).requires_grad_(True)
+    xo, eo = gmp(x, e, r["edge_index"].to(DEV))
+    assert rel_err(xo, r["x_out"]) < TOL and rel_err(eo, r["e_out"]) < TOL
+    torch.autograd.backward([xo, eo], [r["g_xo"].to(DEV), r["g_eo"].to(DEV)])
+    assert rel_l2(x.grad, r["g_x"]) < 2e-3 and _rows_off(x.grad, r["g_x"]) <= 4
+    assert rel_l2(e.grad, r["g_e"]) < 2e-3 and _rows_off(e.grad, r["g_e"]) <= 4
+    for k, p in gmp.named_parameters():
+        assert rel_l2(p.grad, r["g_params"][k]) < 2e-3, k
+    # the whole model, 1 and 3 levels
+    for levels in (1, 3):
+        r = G[f"model_L{levels}"]
+        torch.manual_seed(r["seed"])
+        net = M.BSMS_MeshGraphNet(6, 3, 4, num_levels=levels).to(DEV)
+        multi = M.MultiScaleGraphPreprocessor(levels).create_multiscale_graph(data)
+        na = mesh["node_attr"].to(DEV).requires_grad_(True)
+        out = net(na, mesh["edge_attr"].to(DEV), mesh["edge_index"].to(DEV), multi)
+        assert rel_err(out, r["out"]) < 2e-5
+        (out * r["probe"].to(DEV)).sum().backward()
+        assert rel_l2(na.grad, r["g_node"]) < 2e-3
+        for k, p in net.named_parameters():
+            if k in r["g_params"]:
+                nrm = r["g_params"][k][0]
+                assert abs(float(p.grad.double().norm()) - nrm) <= 5e-3 * max(nrm, 1e-6), k
+            else:
+                assert p.grad is None, k
