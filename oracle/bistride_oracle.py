@@ -1,12 +1,18 @@
 """CPU oracle for the BFS-bistride operators.  TEST INFRASTRUCTURE ONLY (same rules as mgn_oracle.py).
 
-PARITY UNPINNED: upstream ships these components only as CPython 3.11 bytecode
-(/root/reference/models/__pycache__/bistride_ops.cpython-311.pyc and the stale bsms_mgn.cpython-311.pyc); there is no
-source, no test, no golden vector, and the bytecode cannot execute on this image's Python 3.12.  The functions below
-restate the behaviour decoded from the marshal stream (oracle/decode_bistride_pyc.py prints --
-and oracle/bistride_pyc_decoded.txt holds, for readers without the reference checkout -- the
-constants, names and load order the restatement was checked against: hidden width 64, fallback ratio 0.3, the
-cat orders [x_src, x_dst, len] / [x_src, x_dst, e] / [x, agg], pos[dst] - pos[src], `a = a + b` residuals).
+Upstream ships these components only as CPython 3.11 bytecode
+(/root/reference/models/__pycache__/bistride_ops.cpython-311.pyc and the stale bsms_mgn.cpython-311.pyc): no source, no
+test, no golden vector, and the bytecode does not run on this image's Python 3.12.  The functions below restate the
+behaviour decoded from the marshal stream (oracle/decode_bistride_pyc.py prints -- and
+oracle/bistride_pyc_decoded.txt holds -- the constants, names and operand order: hidden width 64, fallback ratio 0.3,
+the cat orders [x_src, x_dst, len] / [x_src, x_dst, e] / [x, agg], pos[dst] - pos[src], `a = a + b` residuals).
+
+PINNING: oracle/pyc311_vm.py is a small interpreter for 3.11 bytecode; oracle/gen_bistride_golden.py uses it to
+EXECUTE the reference's own code objects (real torch / nn.Module objects, torch_scatter stand-in, the reference's real
+models/mlp.py) and records BFS distances, selections, hierarchies, Unpool, WeightedEdgeConv, GMP and BSMS_MeshGraphNet
+outputs with autograd gradients into tests/golden/bistride.pt.  tests/test_bistride_golden.py checks every function
+below against those vectors (integers exact, floats <= 1e-5, gradients <= 1e-4).  What stays unpinned is only the
+torch_scatter boundary (absent package, published semantics restated -- as for mgn_oracle.py).
 "orig :NN" = first line of the code object in the pyc.  Plain torch CPU tensors, Python loops for the BFS.
 """
 from __future__ import annotations

@@ -1,7 +1,8 @@
 """CPU checks of the BFS-bistride oracle (oracle/bistride_oracle.py) and of the host-side mirror of
 `models.bistride_ops` / the older `models.bsms_mgn` design.  The reference ships these components only as
-CPython 3.11 bytecode, so there is no golden vector: the oracle is pinned by known-answer cases worked by hand and by
-an independent nn.Module evaluation of the decoded architecture ("parity unpinned")."""
+CPython 3.11 bytecode; besides the vectors recorded by executing that bytecode (tests/test_bistride_golden.py) the
+oracle is checked here with known-answer cases worked by hand and an independent nn.Module evaluation of the decoded
+architecture."""
 import pytest
 import torch
 import torch.nn.functional as F
