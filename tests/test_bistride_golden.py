@@ -126,3 +126,36 @@ def test_messages_and_config_helper(G):
     net = M.create_bsms_model_from_config(cfg)
     assert (net.num_levels, net.latent_dim) == (G["from_config"]["num_levels"], G["from_config"]["latent_dim"])
     assert sorted(net.state_dict().keys()) == G["from_config"]["keys"]
+
+
+@pytest.mark.skipif(not __import__("os").path.exists("/root/reference/models/__pycache__/bistride_ops.cpython-311.pyc"),
+                    reason="needs the reference checkout (only the container that generated the fixtures has it)")
+def test_fixture_reproduces_from_the_reference_bytecode(G):
+    """Where the reference checkout exists, re-run part of the generator: the bytecode interpreter must reproduce the
+    committed vectors (guards the interpreter and the fixture against drifting apart)."""
+    import sys
+    saved = {k: sys.modules.get(k) for k in ("models", "models.mlp", "torch_scatter", "torch_geometric", "torch_geometric.nn")}
+    saved_path = list(sys.path)
+    try:
+        from oracle import gen_bistride_golden as gen
+        Bm, Sm = gen.load_reference_modules()
+        for r in G["bfs"][:2] + G["bfs"][3:]:
+            assert torch.equal(Bm["BistridePooling"].bfs_distance(r["edge_index"], r["n"], r["start"]), r["dist"])
+        r = G["wec"][0]
+        torch.manual_seed(r["seed"])
+        conv = Bm["WeightedEdgeConv"](128, 128, aggr=r["aggr"])
+        out, w = conv(r["x"], r["edge_index"], r["pos"])
+        assert torch.equal(out, r["out"]) and torch.equal(w, r["w"])
+        import types
+        m = G["mesh"]
+        multi = Sm["MultiScaleGraphPreprocessor"](num_levels=3).create_multiscale_graph(
+            types.SimpleNamespace(edge_index=m["edge_index"], pos=m["pos"]))
+        for a, b in zip(multi["node_indices"], G["model_L3"]["multi"]["node_indices"]):
+            assert torch.equal(a, b)
+    finally:
+        sys.path[:] = saved_path
+        for k, v in saved.items():          # the stand-ins must not leak into the other tests of this process
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
