@@ -17,7 +17,7 @@ INCLUDE = PKG.parent / "include"
 BUILD = PKG / "build"
 LIB = PKG / "libaero_sm100.so"
 
-SOURCES = ["abi.cu", "sort_plan.cu", "segment.cu", "block_simt.cu", "block_umma.cu", "block_umma_bwd.cu",
+SOURCES = ["abi.cu", "sort_plan.cu", "segment.cu", "block_simt.cu", "block_umma.cu", "block_umma_bwd.cu", "block_umma_bwd2.cu",
            "umma_probe.cu", "bistride.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -383,13 +383,16 @@ int umma_block_fwd(const aero_block_desc* d, cudaStream_t st) {
     AERO_CUDA(cudaMemsetAsync(d->agg, 0, (size_t)d->n_nodes * 128 * sizeof(float), st));
   }
   if (d->rows == 0) return AERO_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  AERO_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     AERO_CUDA(cudaFuncSetAttribute(umma_block_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)fwd_smem(UMMA_MAX_L)));
     AERO_CUDA(cudaFuncSetAttribute(umma_block_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)fwd_smem(UMMA_MAX_L)));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   int64_t tiles = cdiv(d->rows, 128);
   int64_t want = cdiv(tiles, FWD_GROUPS);

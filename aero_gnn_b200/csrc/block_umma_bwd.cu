@@ -20,6 +20,7 @@
 // The MMAs of a phase are issued by the elected lane of warp 0 inside a warp-uniform branch (umma.cuh: elect_one),
 // which keeps the descriptors in uniform registers; every staging phase issues all its global loads before its
 // first shared-memory store.
+#include <stdlib.h>
 #include "umma_block.cuh"
 
 namespace aero {
@@ -508,15 +509,26 @@ int umma_block_bwd(const aero_block_desc* d, cudaStream_t st) {
     return AERO_OK;
   }
   a.w_part = reinterpret_cast<float*>(d->workspace);
-  static bool attr_set = false;
-  if (!attr_set) {
+  int grid = bwd_grid_umma(d->rows);
+  // TMA-fed variant (block_umma_bwd2.cu) whenever the forward kept h_0; AERO_BWD_V1=1 keeps the first-generation kernel
+  const char* v1_env = getenv("AERO_BWD_V1");
+  const bool force_v1 = v1_env && v1_env[0] == '1';
+  if (!force_v1 && umma_bwd2_applicable(d)) {
+    int rc = umma_block_bwd2(d, a, grid, st);
+    if (rc) return rc;
+    return launch_reduce_partials(a.w_part + off, grid, pl.total(), d->g_w + off, pl.total() - off, st);
+  }
+  // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  AERO_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     AERO_CUDA(cudaFuncSetAttribute(umma_block_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)bwd_smem(UMMA_MAX_L_BWD)));
     AERO_CUDA(cudaFuncSetAttribute(umma_block_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)bwd_smem(UMMA_MAX_L_BWD)));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  int grid = bwd_grid_umma(d->rows);
   if (d->act == AERO_ACT_RELU) umma_block_bwd_kernel<true><<<grid, BWD_THREADS, bwd_smem(d->L), st>>>(a);
   else umma_block_bwd_kernel<false><<<grid, BWD_THREADS, bwd_smem(d->L), st>>>(a);
   AERO_LAUNCH_CHECK();

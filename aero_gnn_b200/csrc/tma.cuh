@@ -1,0 +1,52 @@
+// tma.cuh -- Tensor Memory Accelerator helpers: tensor maps over [rows,128] bf16 row matrices and the
+// cp.async.bulk.tensor instructions that move one 64-column x 128-row panel of a row tile (umma.cuh) between
+// global memory and the SWIZZLE_128B shared-memory tile format, asynchronously and without any thread touching
+// the data.  Out-of-range rows are zero-filled on load and clipped on store, so the ragged last tile needs no code.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace aero {
+namespace tma {
+
+// host: tensor map of a row-major [rows,128] bf16 matrix, box = 64 columns (128 bytes) x 128 rows, SWIZZLE_128B.
+// Returns 0 on success; the driver entry point is resolved at run time (no link-time dependency on libcuda).
+int make_rows_map(const void* base, int64_t rows, CUtensorMap* out);
+
+__device__ __forceinline__ void prefetch_map(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];\n" ::"l"(tm) : "memory");
+}
+// one panel: columns [64*panel, 64*panel+64) of rows [row0, row0+128) -> dst (16 KB, 1024-byte aligned)
+__device__ __forceinline__ void load_panel(uint32_t dst_saddr, const CUtensorMap* tm, int panel, int row0, uint32_t mbar_saddr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst_saddr),
+      "l"(tm), "r"(panel * 64), "r"(row0), "r"(mbar_saddr)
+      : "memory");
+}
+// whole 128x128 row tile (two panels); the caller has armed the mbarrier with 32768 bytes
+__device__ __forceinline__ void load_tile(uint32_t dst_saddr, const CUtensorMap* tm, int row0, uint32_t mbar_saddr) {
+  load_panel(dst_saddr, tm, 0, row0, mbar_saddr);
+  load_panel(dst_saddr + 16384u, tm, 1, row0, mbar_saddr);
+}
+// hint: bring both panels of the row tile at row0 into L2
+__device__ __forceinline__ void prefetch_tile_l2(const CUtensorMap* tm, int row0) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(tm), "r"(0), "r"(row0) : "memory");
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(tm), "r"(64), "r"(row0) : "memory");
+}
+__device__ __forceinline__ void store_tile(const CUtensorMap* tm, uint32_t src_saddr, int row0) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(tm), "r"(0), "r"(row0),
+               "r"(src_saddr)
+               : "memory");
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(tm), "r"(64), "r"(row0),
+               "r"(src_saddr + 16384u)
+               : "memory");
+}
+__device__ __forceinline__ void store_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+// the issuing thread's bulk stores have finished READING shared memory (the tiles may be overwritten)
+__device__ __forceinline__ void store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+// ... have completed entirely (before the CTA exits)
+__device__ __forceinline__ void store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+
+}  // namespace tma
+}  // namespace aero

@@ -31,6 +31,8 @@ struct UmmaArgs {
 constexpr int UMMA_MAX_L = 2;
 constexpr int UMMA_MAX_L_BWD = 2;
 size_t umma_bwd_workspace_bytes(const aero_block_desc* d);
+// TMA-fed backward (block_umma_bwd2.cu): kept h_0, 1 <= L <= 2
+bool umma_bwd2_applicable(const aero_block_desc* d);
 
 // ---- helpers --------------------------------------------------------------------------------------
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
@@ -359,5 +361,7 @@ static inline UmmaArgs make_uargs(const aero_block_desc* d) {
   a.w_part = nullptr;
   return a;
 }
+
+int umma_block_bwd2(const aero_block_desc* d, UmmaArgs a, int grid, cudaStream_t st);
 
 }  // namespace aero

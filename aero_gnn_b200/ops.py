@@ -381,17 +381,24 @@ def wgrad_into(g_w: torch.Tensor, g_h0: torch.Tensor, rows_in: torch.Tensor) -> 
 
 def block_bwd(prep: PreparedBlock, main, P, idx0, idx1, poff0, poff1, g_out, *, g_agg=None, main_scale=None,
               has_resid_grad=False, g_main_out: Optional[torch.Tensor] = None, kind=None,
-              h0: Optional[torch.Tensor] = None, n_nodes: Optional[int] = None):
+              h0: Optional[torch.Tensor] = None, n_nodes: Optional[int] = None,
+              rowptr: Optional[torch.Tensor] = None):
     """Backward of one fused block; returns (g_main, g_h0, g_w_packed[fp32], W_main slot zero).  With `h0` (the
-    rows kept by block_fwd(h0_out=...)) layer 0 is not recomputed and `P` may be None."""
+    rows kept by block_fwd(h0_out=...)) layer 0 is not recomputed and `P` may be None.  `rowptr` (receiver CSR of
+    the rows, with `g_agg`) lets the TMA-fed kernel take d(beta)'s receiver part as sum_n deg(n) g_agg[n]."""
     _require_cuda(main, P, g_out, h0)
     lib = _l.load()
     if P is None and h0 is None:
         raise RuntimeError("block_bwd needs the pre-projection P or the kept h_0 rows")
     dev, ldt = g_out.device, g_out.dtype
-    if n_nodes is None:
-        n_nodes = P.size(0) if P is not None else (g_agg.size(0) if g_agg is not None else main.size(0))
-    d = _desc(prep, main, None, P, idx0, idx1, poff0, poff1, main_scale=main_scale, n_nodes=n_nodes, like=g_out)
+    if g_agg is not None:
+        n_nodes = g_agg.size(0)      # rows of the receiver-gradient matrix (a partitioned mesh owns fewer than plan.N)
+    elif n_nodes is None:
+        n_nodes = P.size(0) if P is not None else main.size(0)
+    if rowptr is not None and rowptr.numel() < n_nodes + 1:
+        raise RuntimeError("block_bwd: rowptr is shorter than the receiver-gradient matrix")
+    d = _desc(prep, main, None, P, idx0, idx1, poff0, poff1, main_scale=main_scale, n_nodes=n_nodes, like=g_out,
+              rowptr=rowptr)
     d.h0 = h0.data_ptr() if h0 is not None else None
     rows = main.size(0)
     g_main = g_main_out if g_main_out is not None else torch.empty((rows, D), dtype=main.dtype, device=dev)

@@ -216,7 +216,8 @@ class PartitionedStackFn(torch.autograd.Function):
             agg_eff = agg if scale is None else agg * scale[:, None]
             ops.wgrad_into(g_wn, g_h0n, agg_eff.to(dt))
             G_e, g_h0e, g_we = ops.block_bwd(pe, e, P, plan.src, plan.dst, 0, D, G_e, g_agg=g_agg, has_resid_grad=True,
-                                             g_main_out=G_e, kind="edge_bwd", h0=h0e, n_nodes=plan.N)
+                                             g_main_out=G_e, kind="edge_bwd", h0=h0e, n_nodes=plan.N,
+                                             rowptr=plan.rowptr)
             ops.wgrad_into(g_we, g_h0e, e)
             g_psd = torch.empty((plan.N, 2 * D), dtype=dt, device=e.device)   # [g_P_s | g_P_d] over local rows
             ops.segment_reduce(g_h0e, plan.sptr, plan.sperm, plan.N, out=g_psd[:, :D])

@@ -295,7 +295,7 @@ class MGNStackFn(torch.autograd.Function):
             # edge block: total gradient of e' = G_e + g_agg[receiver]
             G_e, g_h0e, g_we = ops.block_bwd(pe, e, P, plan.src, plan.dst, 0, D, G_e, g_agg=g_agg,
                                              has_resid_grad=True, g_main_out=G_e, kind="edge_bwd", h0=h0e,
-                                             n_nodes=plan.N)
+                                             n_nodes=plan.N, rowptr=plan.rowptr)
             ops.wgrad_into(g_we, g_h0e, e)
             # gradients of the gathered projections: segmented sums by sender and by receiver
             # (both land in one [N, 2D] matrix, so the products with W_s | W_d are single K = 2D GEMMs)
