@@ -59,24 +59,28 @@ __device__ __forceinline__ uint32_t relu_mask_bf16x2(uint32_t v, uint32_t h) {
 }
 
 // G_{m-1} = acc * act'(H_{m-1}) for one (row, 32-column chunk), written in place over H_{m-1}
+// (the stores wait for `bar`: the weight-gradient GEMM still reads H_{m-1} while the values are computed)
 template <bool RELU>
-__device__ __forceinline__ void mask_epilogue_chunk(uint32_t taddr, uint8_t* Ht, int row, int c, int act) {
+__device__ __forceinline__ void mask_epilogue_chunk(uint32_t taddr, uint8_t* Ht, int row, int c, int act, uint32_t bar,
+                                                    uint32_t parity) {
   float v[32];
   tmem_ld32(taddr, v);
   if (RELU) {
+    uint4 o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      uint8_t* p = Ht + tile_chunk_off(row, c * 4 + j);
-      const uint4 h4 = *reinterpret_cast<const uint4*>(p);
-      uint4 o;
-      o.x = relu_mask_bf16x2(pack_bf16(v[8 * j + 0], v[8 * j + 1]), h4.x);
-      o.y = relu_mask_bf16x2(pack_bf16(v[8 * j + 2], v[8 * j + 3]), h4.y);
-      o.z = relu_mask_bf16x2(pack_bf16(v[8 * j + 4], v[8 * j + 5]), h4.z);
-      o.w = relu_mask_bf16x2(pack_bf16(v[8 * j + 6], v[8 * j + 7]), h4.w);
-      *reinterpret_cast<uint4*>(p) = o;
+      const uint4 h4 = *reinterpret_cast<const uint4*>(Ht + tile_chunk_off(row, c * 4 + j));
+      o[j].x = relu_mask_bf16x2(pack_bf16(v[8 * j + 0], v[8 * j + 1]), h4.x);
+      o[j].y = relu_mask_bf16x2(pack_bf16(v[8 * j + 2], v[8 * j + 3]), h4.y);
+      o[j].z = relu_mask_bf16x2(pack_bf16(v[8 * j + 4], v[8 * j + 5]), h4.z);
+      o[j].w = relu_mask_bf16x2(pack_bf16(v[8 * j + 6], v[8 * j + 7]), h4.w);
     }
+    mbar_wait(bar, parity);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(Ht + tile_chunk_off(row, c * 4 + j)) = o[j];
   } else {
     mask_by_act_grad(v, Ht, row, c, act);
+    mbar_wait(bar, parity);
     store_row32(Ht, row, c, v);
   }
 }
@@ -92,8 +96,8 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
   uint8_t* X = Wslot + 2 * TILE_BYTES;                      // 4 activation tiles, roles rotate
   float* vec = reinterpret_cast<float*>(X + (size_t)4 * TILE_BYTES);
   float* red = vec + (UMMA_MAX_L_BWD + 3) * 128;             // [4 chunks][128 rows] float4 (LayerNorm row sums)
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 2048);  // [0] mma, [1..2] weight slots, [3] h0, [4] g_out, [5] reload
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 6);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 2048);  // [0] mma, [1..2] weight slots, [3] h0, [4] g_out, [5] reload, [6] dW
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 7);
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int q = wid & 3;         // TMEM lane quarter
@@ -104,7 +108,7 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
     for (int i = tid; i < (L + 3) * 128; i += B2_THREADS) vec[i] = vs[i];
   }
   if (tid == 0) {
-    for (int i = 0; i < 6; ++i) mbar_init(smem_u32(&mbar[i]), 1);
+    for (int i = 0; i < 7; ++i) mbar_init(smem_u32(&mbar[i]), 1);
     fence_mbar_init();
   }
   if (tid < 32) tmem_alloc<512>(tmem_slot);
@@ -114,7 +118,7 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32);
   const uint32_t bar_mma = smem_u32(&mbar[0]);
-  const uint32_t bar_h0 = smem_u32(&mbar[3]), bar_g = smem_u32(&mbar[4]), bar_r = smem_u32(&mbar[5]);
+  const uint32_t bar_h0 = smem_u32(&mbar[3]), bar_g = smem_u32(&mbar[4]), bar_r = smem_u32(&mbar[5]), bar_dw = smem_u32(&mbar[6]);
   const uint32_t x_s = smem_u32(X);
   const uint32_t w_s = smem_u32(Wslot);
   const int act = RELU ? AERO_ACT_RELU : a.act;
@@ -123,33 +127,31 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
 
   // ---- weight streaming, TMA and MMA issue belong to warp 0 (warp-uniform branch; one elected lane touches the hardware) ----
   const bool w0 = __shfl_sync(0xffffffffu, wid, 0) == 0;
-  int slot_mat[2] = {-1, -1};
-  bool slot_pending[2] = {false, false};
-  uint32_t slot_phase[2] = {0, 0};
+  // slot s = m & 1 holds matrix m.  State of both slots in one register (no local-memory arrays): per slot 3 bits
+  // (resident matrix + 1), 1 bit (transfer in flight), 1 bit (mbarrier phase); slot s at bit 8*s.
+  uint32_t wst = 0;
   auto prefetch = [&](int m) {
-    int s = m & 1;
-    if (slot_mat[s] == m) return;
-    uint32_t bar = smem_u32(&mbar[1 + s]);
-    if (slot_pending[s]) {   // a transfer nobody waited for: consume its phase before the barrier is re-armed
-      mbar_wait(bar, slot_phase[s]);
-      slot_phase[s] ^= 1;
-      slot_pending[s] = false;
+    const int s = m & 1, sh = 8 * s;
+    if ((int)((wst >> sh) & 7u) == m + 1) return;
+    const uint32_t bar = smem_u32(&mbar[1 + s]);
+    if ((wst >> (sh + 3)) & 1u) {   // a transfer nobody waited for: consume its phase before the barrier is re-armed
+      mbar_wait(bar, (wst >> (sh + 4)) & 1u);
+      wst ^= 1u << (sh + 4);
     }
     if (elect_one()) {
       mbar_expect_tx(bar, TILE_BYTES);
       bulk_g2s(w_s + (uint32_t)s * TILE_BYTES, a.prep + (size_t)m * TILE_BYTES, TILE_BYTES, bar);
     }
     __syncwarp();
-    slot_mat[s] = m;
-    slot_pending[s] = true;
+    wst = (wst & ~(15u << sh)) | ((uint32_t)(m + 1) << sh) | (8u << sh);
   };
   auto acquire = [&](int m) -> uint32_t {
-    int s = m & 1;
-    if (slot_mat[s] != m) prefetch(m);
-    if (slot_pending[s]) {
-      mbar_wait(smem_u32(&mbar[1 + s]), slot_phase[s]);
-      slot_phase[s] ^= 1;
-      slot_pending[s] = false;
+    const int s = m & 1, sh = 8 * s;
+    if ((int)((wst >> sh) & 7u) != m + 1) prefetch(m);
+    if ((wst >> (sh + 3)) & 1u) {
+      mbar_wait(smem_u32(&mbar[1 + s]), (wst >> (sh + 4)) & 1u);
+      wst ^= 1u << (sh + 4);
+      wst &= ~(8u << sh);
     }
     return w_s + (uint32_t)s * TILE_BYTES;
   };
@@ -178,12 +180,16 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
     prefetch(2);   // L >= 1: matrix 2 exists (W_2 or W_out)
   }
 
-  uint32_t ph_mma = 0, ph_h0 = 0, ph_g = 0, ph_r = 0;
+  uint32_t ph_mma = 0, ph_h0 = 0, ph_g = 0, ph_r = 0, ph_dw = 0;
   bool first_tile = true;
   float db[UMMA_MAX_L_BWD + 1][2];
 #pragma unroll
   for (int i = 0; i <= UMMA_MAX_L_BWD; ++i) db[i][0] = db[i][1] = 0.f;
   float dbet0 = 0.f, dbet1 = 0.f, db00 = 0.f, db01 = 0.f, dgam = 0.f;
+
+  // receiver id of this thread's row, fetched one tile ahead (its latency never meets a dependent load)
+  int dst_next = -1;
+  if (a.g_agg && (int64_t)blockIdx.x * 128 + row < a.rows) dst_next = __ldg(a.idx1 + (int64_t)blockIdx.x * 128 + row);
 
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t row0 = tile * 128;
@@ -193,7 +199,12 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
     const int next_r0 = (int)((tile + gridDim.x) * 128);
     // this thread's piece of the receiver-gradient row (fp32): added to the incoming gradient and to the residual
     const float* gag = nullptr;
-    if (a.g_agg && valid) gag = a.g_agg + (size_t)a.idx1[row0 + row] * 128 + ch * 32;
+    if (dst_next >= 0) {
+      gag = a.g_agg + (size_t)dst_next * 128 + ch * 32;
+      prefetch_l1(gag);   // 128 bytes = one line; read three GEMMs later (LayerNorm backward) and again by the last epilogue
+    }
+    dst_next = -1;
+    if (a.g_agg && has_next && (int64_t)next_r0 + row < a.rows) dst_next = __ldg(a.idx1 + (int64_t)next_r0 + row);
 
     // Tiles released by backward phase `done` (its MMAs have completed and every warp has passed the phase's closing
     // barrier, so neither the tensor core nor a column-sum reader still touches them) receive what the TMA engine is
@@ -362,9 +373,12 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
         if (elect_one()) {
           release(m + 1);
           const uint32_t g_addr = x_s + (uint32_t)tg * TILE_BYTES;
-          issue_gemm(tmem_base + (uint32_t)(128 * m), g_addr, true, x_s + (uint32_t)th * TILE_BYTES, true, !first_tile);   // dW_m += G^T H
+          // the data gradient first, with its own completion barrier: the epilogue starts on it while the weight
+          // gradient runs, and only its in-place stores over H_{m-1} (the dW operand) wait for the second barrier
           issue_gemm(tmem_base, g_addr, false, wa, true, false);                                                           // G W_m
           mma_commit(bar_mma);
+          issue_gemm(tmem_base + (uint32_t)(128 * m), g_addr, true, x_s + (uint32_t)th * TILE_BYTES, true, !first_tile);   // dW_m += G^T H
+          mma_commit(bar_dw);
         }
         __syncwarp();
         prefetch(m - 1);
@@ -382,7 +396,8 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
       mbar_wait(bar_mma, ph_mma);
       ph_mma ^= 1;
       fence_after_sync();
-      mask_epilogue_chunk<RELU>(tlane, X + (size_t)th * TILE_BYTES, row, ch, act);
+      mask_epilogue_chunk<RELU>(tlane, X + (size_t)th * TILE_BYTES, row, ch, act, bar_dw, ph_dw);
+      ph_dw ^= 1;
       fence_before_sync();
       fence_async_smem();
       __syncthreads();
@@ -492,7 +507,18 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
       const int64_t n0 = (int64_t)blockIdx.x * per;
       const int64_t n1 = (n0 + per) < a.n_nodes ? (n0 + per) : a.n_nodes;
       const int col = tid & 127;
-      for (int64_t n = n0 + (tid >> 7); n < n1; n += 4) {
+      int64_t n = n0 + (tid >> 7);
+      for (; n + 28 < n1; n += 32) {   // eight rows per trip, all loads issued before the first use
+        float g[8], c[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          g[u] = __ldg(a.g_agg + (size_t)(n + 4 * u) * 128 + col);
+          c[u] = (float)(__ldg(a.rowptr + n + 4 * u + 1) - __ldg(a.rowptr + n + 4 * u));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = fmaf(c[u], g[u], acc);
+      }
+      for (; n < n1; n += 4) {
         const float cnt = (float)(a.rowptr[n + 1] - a.rowptr[n]);
         acc = fmaf(cnt, __ldg(a.g_agg + (size_t)n * 128 + col), acc);
       }
@@ -528,7 +554,7 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
 
 // ---- host side ------------------------------------------------------------------------------------
 static size_t bwd2_smem() {
-  return 1024 + (size_t)6 * TILE_BYTES + (size_t)(UMMA_MAX_L_BWD + 3) * 512 + 8192 + 6 * 8 + 16;
+  return 1024 + (size_t)6 * TILE_BYTES + (size_t)(UMMA_MAX_L_BWD + 3) * 512 + 8192 + 7 * 8 + 16;
 }
 
 bool umma_bwd2_applicable(const aero_block_desc* d) {

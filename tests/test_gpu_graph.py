@@ -69,3 +69,33 @@ def test_graph_replay_matches_eager(dtype):
         assert torch.equal(a, b)
     assert l0 < l1
     del ref_gx0, ref_ge0, ref_gw
+
+
+def test_replays_rewrite_gradients_instead_of_accumulating():
+    """GraphedStep(leaves=...) resets the warm-up's gradients before the capture, so two replays on the same inputs
+    leave the same gradients (not doubled), equal to one eager step, in the static tensors of `g.grads`."""
+    from aero_gnn_b200.graphs import GraphedStep
+    from aero_gnn_b200.models._common import run_layers
+    net, plan, x0, e0, gx = _setup(torch.bfloat16)
+    params = list(net.layers.parameters())
+
+    def step():                                   # note: does NOT clear gradients itself
+        x, e = run_layers(net.layers, plan, x0, e0)
+        torch.autograd.backward([x], [gx])
+        return x.detach()
+
+    g = GraphedStep(step, leaves=[x0, e0, *params])
+    g()
+    torch.cuda.synchronize()
+    first = [t.clone() for t in g.grads]
+    g()
+    torch.cuda.synchronize()
+    for a, b, leaf in zip(first, g.grads, [x0, e0, *params]):
+        assert torch.equal(a, b)
+        assert leaf.grad is b                     # the static tensor is the leaf's .grad
+    for t in [x0, e0, *params]:
+        t.grad = None
+    step()
+    torch.cuda.synchronize()
+    for a, leaf in zip(first, [x0, e0, *params]):
+        assert torch.equal(a, leaf.grad)
