@@ -17,6 +17,7 @@
 //     tensor pipe and the LSU/ALU pipes busy.  Epilogue loops are chunked (32 columns) and not unrolled across
 //     chunks so the instruction footprint stays inside the instruction cache.
 #include "umma_block.cuh"
+#include "tma.cuh"
 
 namespace aero {
 
@@ -47,8 +48,12 @@ __global__ void umma_prepare_kernel(const float* __restrict__ w, int L, uint8_t*
 // =============================================================================================
 // forward
 // =============================================================================================
+// tm_main / tm_resid / tm_out / tm_h0: SWIZZLE_128B tensor maps of the bf16 row matrices a.main, a.resid, a.out, a.h0
+// (tma.cuh); a map whose matrix is absent (fp32 main, no residual, no h0) is a copy of tm_out and never used.
 template <bool RELU>
-__global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs a) {
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+umma_block_fwd_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_resid,
+                      const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_h0) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   const int L = a.L;
@@ -59,8 +64,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
   float2* red = reinterpret_cast<float2*>(sidx + FWD_GROUPS * 256);            // [group][2][128] LN partials
   uint32_t* segmask = reinterpret_cast<uint32_t*>(red + FWD_GROUPS * 256);     // [group][8]: 4 masks + 2 flags
   int* segs = reinterpret_cast<int*>(segmask + FWD_GROUPS * 8);                // [group][132]: heads + count
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(segs + FWD_GROUPS * 132);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + FWD_GROUPS);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(segs + FWD_GROUPS * 132);       // [group][3]: mma, main rows, residual rows
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 3 * FWD_GROUPS);
 
   const int tid = threadIdx.x, grp = tid / FWD_GT, gt = tid % FWD_GT, lane = tid & 31;
   const int gw = gt >> 5;            // warp inside the group, 0..7
@@ -78,7 +83,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
     for (int i = tid; i < (L + 3) * 128; i += FWD_THREADS) vec[i] = vs[i];
   }
   if (tid == 0) {
-    for (int w = 0; w < FWD_GROUPS; ++w) mbar_init(smem_u32(&mbar[w]), 1);
+    for (int w = 0; w < 3 * FWD_GROUPS; ++w) mbar_init(smem_u32(&mbar[w]), 1);
     fence_mbar_init();
   }
   if (tid < 32) tmem_alloc<FWD_GROUPS * 128>(tmem_slot);
@@ -92,7 +97,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
   uint8_t* A = Abuf + (size_t)grp * TILE_BYTES;
   const uint32_t a_s = smem_u32(A);
   const uint32_t w_s = smem_u32(Wimg);
-  const uint32_t bar_s = smem_u32(&mbar[grp]);
+  const uint32_t bar_s = smem_u32(&mbar[3 * grp]);
+  const uint32_t bar_in = smem_u32(&mbar[3 * grp + 1]), bar_res = smem_u32(&mbar[3 * grp + 2]);
+  uint32_t ph_in = 0, ph_res = 0;
+  const bool tma_main = !a.main_f32;
   int* sidx0 = sidx + grp * 256;
   int* sidx1 = sidx0 + 128;
   float2* gred = red + grp * 256;
@@ -106,9 +114,26 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
   for (int64_t tile = (int64_t)blockIdx.x * FWD_GROUPS + grp; tile < tiles; tile += (int64_t)gridDim.x * FWD_GROUPS) {
     const int64_t row0 = tile * 128;
     const int nrows = (int)((a.rows - row0) < 128 ? (a.rows - row0) : 128);
+    if (gw0) {   // the previous tile's output store has finished reading the activation tile
+      if (elect_one()) tma::store_wait_read();
+      __syncwarp();
+    }
     named_sync(bar_id, FWD_GT);   // previous tile of this group fully consumed
-    if (a.main_f32) stage_rows<true, FWD_GT>(A, a.main, a.main_scale, row0, nrows, gt);
-    else stage_rows<false, FWD_GT>(A, a.main, nullptr, row0, nrows, gt);
+    if (tma_main) {
+      // bf16 rows: fetched by the TMA engine straight into the UMMA tile format while the index work below runs;
+      // the group's next tile is pulled into L2 at the same time
+      if (gw0) {
+        if (elect_one()) {
+          mbar_expect_tx(bar_in, TILE_BYTES);
+          tma::load_tile(a_s, &tm_main, (int)row0, bar_in);
+          const int64_t nr0 = (tile + (int64_t)gridDim.x * FWD_GROUPS) * 128;
+          if (nr0 < a.rows) tma::prefetch_tile_l2(&tm_main, (int)nr0);
+        }
+        __syncwarp();
+      }
+    } else {
+      stage_rows<true, FWD_GT>(A, a.main, a.main_scale, row0, nrows, gt);
+    }
     if (gt < 128) {
       int64_t r = row0 + gt;
       bool ok = gt < nrows;
@@ -157,16 +182,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
       }
     }
     // pull this group's next tile into L2 while the current one computes
-    {
+    if (a.main_f32) {
       const int64_t r = (tile + (int64_t)gridDim.x * FWD_GROUPS) * 128 + (gt >> 1);
       if (r < a.rows) {
-        if (a.main_f32) {
-          const float* p = reinterpret_cast<const float*>(a.main) + r * 128 + (gt & 1) * 64;
-          prefetch_l2(p);
-          prefetch_l2(p + 32);
-        } else {
-          prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(a.main) + r * 128 + (gt & 1) * 64);
-        }
+        const float* p = reinterpret_cast<const float*>(a.main) + r * 128 + (gt & 1) * 64;
+        prefetch_l2(p);
+        prefetch_l2(p + 32);
       }
     }
     // gather indices of the NEXT tile: their pre-projected rows are prefetched into L2 after this tile's first
@@ -182,6 +203,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
 
     for (int layer = 0; layer <= L + 1; ++layer) {
       if (gw0) {   // first warp of the group, warp-uniform branch; one elected lane issues
+        if (layer == 0 && tma_main) {
+          mbar_wait(bar_in, ph_in);
+          ph_in ^= 1;
+        }
         fence_after_sync();
         if (elect_one()) {
           issue_gemm(tacc, a_s, false, w_s + (uint32_t)layer * TILE_BYTES, false, false);
@@ -189,15 +214,25 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
         }
         __syncwarp();
       }
-      if (layer == 1 && a.h0) {
-        // keep h_0 for the backward: the tile is copied out (coalesced) while GEMM 1 reads it; the group barrier
-        // keeps the next epilogue's writes behind the slowest reader and costs nothing under the MMA
-        unstage_rows<FWD_GT>(A, a.h0, row0, nrows, gt);
-        named_sync(bar_id, FWD_GT);
+      if (layer == 1 && a.h0 && gw0) {
+        // keep h_0 for the backward: a TMA store reads the tile while GEMM 1 does
+        if (elect_one()) {
+          tma::store_tile(&tm_h0, a_s, (int)row0);
+          tma::store_commit();
+        }
+        __syncwarp();
       }
       mbar_wait(bar_s, phase);
       phase ^= 1;
       fence_after_sync();
+      if (layer == 1 && a.h0) {
+        // the next epilogue overwrites the tile: behind the store's reads (long finished; the barrier is the hand-off)
+        if (gw0) {
+          if (elect_one()) tma::store_wait_read();
+          __syncwarp();
+        }
+        named_sync(bar_id, FWD_GT);
+      }
 
       if (layer == 0) {
         // the MMA that read A has completed: A now receives the coalesced gather P_s[src] + P_d[dst], then each
@@ -220,8 +255,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
         // ---- output epilogue: bias, LayerNorm, residual ----
         const float* bo = vec + L * 128;
         float mean = 0.f, rstd = 1.f;
-        // GEMM_out has consumed A: stage the residual rows into it (coalesced); visible after the next group barrier
-        if (a.resid) stage_rows<false, FWD_GT>(A, a.resid, nullptr, row0, nrows, gt);
+        // GEMM_out has consumed A: the residual rows are fetched into it by the TMA engine under the statistics pass
+        if (a.resid && gw0) {
+          if (elect_one()) {
+            mbar_expect_tx(bar_res, TILE_BYTES);
+            tma::load_tile(a_s, &tm_resid, (int)row0, bar_res);
+          }
+          __syncwarp();
+        }
         if (a.use_ln) {
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
 #pragma unroll 1
@@ -246,7 +287,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
         }
         const float* gam = vec + (L + 1) * 128;
         const float* bet = vec + (L + 2) * 128;
-        if (!a.use_ln && a.resid) named_sync(bar_id, FWD_GT);   // (with LayerNorm the statistics barrier covers it)
+        if (a.resid) {
+          mbar_wait(bar_res, ph_res);
+          ph_res ^= 1;
+        }
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
           const int c = hf * 2 + cc;
@@ -272,9 +316,16 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
           store_row32(A, row, c, v);
         }
         fence_before_sync();
+        fence_async_smem();
         named_sync(bar_id, FWD_GT);
-        // coalesced store of the output tile
-        unstage_rows<FWD_GT>(A, a.out, row0, nrows, gt);
+        // the output tile leaves through a TMA store (rows beyond the matrix are clipped)
+        if (gw0) {
+          if (elect_one()) {
+            tma::store_tile(&tm_out, a_s, (int)row0);
+            tma::store_commit();
+          }
+          __syncwarp();
+        }
         if (a.agg) {
           // receiver sums over the bf16-rounded rows: one warp per CSR segment (segments k = gw, gw+8, ..),
           // lane = 4 columns, rows in order
@@ -298,6 +349,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) umma_block_fwd_kernel(UmmaArgs
         }
       }
     }
+  }
+  if (gw0) {
+    if (elect_one()) tma::store_wait_all();
+    __syncwarp();
   }
   fence_before_sync();
   __syncthreads();
@@ -361,7 +416,7 @@ int umma_prepare(const float* w, int L, void* prepared, cudaStream_t st) {
 
 static size_t fwd_smem(int L) {
   return 1024 + (size_t)(L + 2 + FWD_GROUPS) * TILE_BYTES + (size_t)(L + 3) * 512 +
-         (size_t)FWD_GROUPS * (1024 + 2048 + 32 + 528 + 8) + 16;
+         (size_t)FWD_GROUPS * (1024 + 2048 + 32 + 528 + 24) + 16;
 }
 
 size_t umma_block_workspace_bytes(const aero_block_desc* d, int backward) {
@@ -397,8 +452,18 @@ int umma_block_fwd(const aero_block_desc* d, cudaStream_t st) {
   int64_t tiles = cdiv(d->rows, 128);
   int64_t want = cdiv(tiles, FWD_GROUPS);
   int grid = (int)(want < sm_count() ? want : sm_count());
-  if (d->act == AERO_ACT_RELU) umma_block_fwd_kernel<true><<<grid, FWD_THREADS, fwd_smem(d->L), st>>>(a);
-  else umma_block_fwd_kernel<false><<<grid, FWD_THREADS, fwd_smem(d->L), st>>>(a);
+  CUtensorMap tm_main, tm_resid, tm_out, tm_h0;
+  if (tma::make_rows_map(d->out, d->rows, &tm_out) ||
+      tma::make_rows_map(d->main_f32 ? d->out : d->main, d->rows, &tm_main) ||
+      tma::make_rows_map(d->resid ? d->resid : d->out, d->rows, &tm_resid) ||
+      tma::make_rows_map(d->h0 ? d->h0 : d->out, d->rows, &tm_h0)) {
+    set_error("umma_block_fwd: cuTensorMapEncodeTiled failed (row matrices must be 16-byte aligned)");
+    return AERO_ECUDA;
+  }
+  if (d->act == AERO_ACT_RELU)
+    umma_block_fwd_kernel<true><<<grid, FWD_THREADS, fwd_smem(d->L), st>>>(a, tm_main, tm_resid, tm_out, tm_h0);
+  else
+    umma_block_fwd_kernel<false><<<grid, FWD_THREADS, fwd_smem(d->L), st>>>(a, tm_main, tm_resid, tm_out, tm_h0);
   AERO_LAUNCH_CHECK();
   if (d->agg) return launch_agg_fixup(a.agg_part, d->rowptr, d->agg, d->rows, d->n_nodes, 128, d->idx1, st);
   return AERO_OK;
