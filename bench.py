@@ -109,29 +109,92 @@ def kernel_alg_flops(kind, E, N, L=2):
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_port_step(nu, nv, threads):
-    """The reference algorithm (oracle port, torch CPU fp32 + autograd) on a bounded wing sub-mesh; returns
-    (edges_per_second, sample description).  The only place besides tests/ and smoke() that runs oracle/."""
+# CPU arm: the reference's own implementation of the path on the host cores.
+#   kind "reference": the UNMODIFIED reference module models/mgnLayer.py:MeshGraphNetLayer from oracle/_ref/ (byte
+#                     copies made by oracle/make_ref.py where the upstream checkout exists; torch_scatter /
+#                     torch_geometric stood in by oracle/standins.py), config.yaml kwargs, fp32, all host threads;
+#   kind "port":      oracle/mgn_oracle.py, only when oracle/_ref/ is absent.
+# One CPU "step" = ONE processor layer forward+backward on a spanwise slab of the C5 wing mesh (same generator, same
+# nu = 1000 section; the slab is sized so the whole run fits a time budget); the 15-layer processor is 15 independent-
+# weight copies of that layer (models/mgn.py:127-128), so edges/s of the processor = E_slab / (15 t_layer)
+# ("C5 on CPU: 1 layer timed x15 extrapolation allowed").  This is the only place besides tests/ and
+# smoke() that executes anything under oracle/.
+LAYER_KW = dict(num_hidden_layers_node_processor=2, num_hidden_layers_edge_processor=2, activation_fn="relu",
+                use_layer_norm=True, aggregation="add", do_concat_trick=True)
+
+
+def cpu_layer_step(nu, nv, threads):
+    """-> (step(), E, kind, description): one reference processor layer fwd+bwd on the nu x nv wing slab."""
+    import contextlib
     from aero_gnn_b200.meshes import wing_surface_mesh
-    from oracle import mgn_oracle as O
-    import aero_gnn_b200.models as M
+    from oracle import make_ref, standins
     torch.set_num_threads(threads)
     mesh = wing_surface_mesh(nu, nv)
-    torch.manual_seed(0)
-    net = M.MeshGraphNet(6, 4, 5, **CFG)
-    sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    N, E = mesh.num_nodes, mesh.num_edges
     g = torch.Generator().manual_seed(1234)
-    x0 = torch.randn(mesh.num_nodes, D, generator=g).requires_grad_(True)
-    e0 = torch.randn(mesh.num_edges, D, generator=g).requires_grad_(True)
+    x0 = torch.randn(N, D, generator=g).requires_grad_(True)
+    e0 = torch.randn(E, D, generator=g).requires_grad_(True)
+    gx, ge = torch.ones(N, D), torch.ones(E, D)
+    torch.manual_seed(0)
+    if make_ref.available():
+        standins.install(os.path.join(ROOT, "oracle", "_ref"))
+        from models.mgnLayer import MeshGraphNetLayer          # the reference's own class, unmodified
+        layer = MeshGraphNetLayer(D, D, D, **LAYER_KW)
+        params = list(layer.parameters())
 
-    def step():
-        x, e = x0, e0
-        for i in range(CFG["processor_size"]):
-            x, e = O.mgn_layer(sd, f"layers.{i}.", x, e, mesh.edge_index, "add")
-        params = [v for k, v in sd.items() if k.startswith("layers.")]
-        torch.autograd.grad(x.sum() + e.sum(), [x0, e0] + params)
+        def step():
+            for p in params:
+                p.grad = None
+            x0.grad = e0.grad = None
+            with contextlib.redirect_stdout(sys.stderr):       # mgnLayer.py:200 prints once when CUDA is visible
+                x, e = layer(x0, e0, mesh.edge_index)
+            torch.autograd.backward([x, e], [gx, ge])
+        kind = "reference"
+        what = "unmodified reference models/mgnLayer.py MeshGraphNetLayer (oracle/_ref, torch_scatter stand-in)"
+    else:
+        import aero_gnn_b200.models as M
+        from oracle import mgn_oracle as O
+        net = M.MeshGraphNetLayer(D, D, D, **LAYER_KW)
+        sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
 
-    return step, mesh.num_edges, f"wing {nu}x{nv}: N={mesh.num_nodes} E={mesh.num_edges}, fp32, torch CPU autograd"
+        def step():
+            x, e = O.mgn_layer(sd, "", x0, e0, mesh.edge_index, "add")
+            torch.autograd.grad([x, e], [x0, e0] + list(sd.values()), [gx, ge])
+        kind = "port"
+        what = "oracle/mgn_oracle.py port (oracle/_ref absent)"
+    desc = (f"one processor layer fwd+bwd x15 (15 independent-weight layers), wing slab {nu}x{nv}: N={N} E={E}, fp32, "
+            f"torch CPU autograd, {threads} threads; {what}")
+    return step, E, kind, desc
+
+
+def cpu_arm(steps, warmup, budget_s, threads):
+    """Times `steps` CPU steps after `warmup`; the slab is sized from a probe so the run takes about budget_s.
+    -> dict(value edges/s of the 15-layer processor, ms_per_step, kind, sample)."""
+    nu = 1000
+    probe, E_p, _, _ = cpu_layer_step(nu, 24, threads)
+    probe()
+    t0 = time.perf_counter()
+    probe()
+    per_edge = (time.perf_counter() - t0) / E_p
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        avail = 64 << 30
+    nv_time = budget_s / max(steps + warmup, 1) / per_edge / (6 * nu)
+    nv_mem = 0.35 * avail / (6 * nu * 128 * 4 * 30)            # ~30 live [E,128] fp32 tensors per layer fwd+bwd
+    nv = int(max(24, min(1000, nv_time, nv_mem)))
+    del probe
+    step, E, kind, desc = cpu_layer_step(nu, nv, threads)
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    t = sum(ts) / len(ts)
+    return {"value": E / (15.0 * t), "ms_per_step": t * 1e3, "kind": kind, "sample": desc, "E": E,
+            "ms_min": min(ts) * 1e3, "ms_max": max(ts) * 1e3, "full_mesh": nv == 1000}
 
 
 def workload_desc(N, E):
@@ -143,25 +206,21 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    nu, nv = 120, 60
-    step, E, desc = cpu_port_step(nu, nv, threads)
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / args.steps
-    val = E / dt
-    line = {"impl": "reference", "metric": "MGN-15 processor edges/sec (fwd+bwd)", "value": val, "unit": "edges/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+    r = cpu_arm(args.steps, args.warmup, 150.0, threads)
+    N, E = args.nu * args.nv, 2 * args.nu * (3 * args.nv - 2)
+    line = {"impl": "reference", "metric": "MGN-15 processor edges/sec (fwd+bwd)", "value": r["value"], "unit": "edges/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_desc(args.nu * args.nv, 2 * args.nu * (3 * args.nv - 2)),
-                       "parallelism": "host cores (torch CPU threads)",
-                       "sample": "each step = the same 15-step fwd+bwd on a bounded sub-mesh of the same generator: " + desc},
-            "cpu_baseline": {"value": val, "unit": "edges/s", "cores": threads, "kind": "port", "sample": desc},
-            "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "config": {"workload": workload_desc(N, E), "parallelism": parallelism_desc(world)},
+            "cpu_baseline": {"value": r["value"], "unit": "edges/s", "cores": threads, "kind": r["kind"],
+                             "sample": r["sample"], "step_ms_min_max": [r["ms_min"], r["ms_max"]]},
+            "e2e": {"value": r["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def parallelism_desc(world):
+    return "single" if world == 1 else f"receiver-block partition x{world} + halo exchange"
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -219,7 +278,6 @@ def main():
             x0.grad = e0.grad = None
             x, e = run_layers(net.layers, plan, x0, e0)
             torch.autograd.backward([x], [gx])
-        parallelism = "single"
     else:
         from aero_gnn_b200.partition import PartitionedProcessor
         pp = PartitionedProcessor(mesh.edge_index, N, rank, world, dev)
@@ -234,7 +292,6 @@ def main():
             x, e = pp.run(net.layers, x0, e0)
             torch.autograd.backward([x], [gx])
             pp.allreduce_grads(net.layers.parameters())
-        parallelism = f"receiver-block partition x{world} + halo exchange"
 
     def sync_all():
         torch.cuda.synchronize()
@@ -408,19 +465,15 @@ def main():
     cpu = None
     if not args.no_cpu and world == 1:
         threads = os.cpu_count() or 1
-        step, Es, desc = cpu_port_step(120, 60, threads)
-        step()
-        t0 = time.perf_counter()
-        step()
-        cs = time.perf_counter() - t0
-        cpu = {"value": Es / cs, "unit": "edges/s", "cores": threads, "kind": "port", "sample": desc}
+        r = cpu_arm(3, 1, 20.0, threads)       # bounded: ~20 s of host work (1 warm-up + 3 timed layer steps)
+        cpu = {"value": r["value"], "unit": "edges/s", "cores": threads, "kind": r["kind"], "sample": r["sample"]}
 
     line = {"metric": "MGN-15 processor edges/sec (fwd+bwd)", "value": value, "unit": "edges/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "edge_steps_per_s": 15 * value,
             "config": {"workload": workload_desc(N, E),
-                       "parallelism": parallelism, "l2": "inputs (>1.7 GB of latents per step) are larger than L2",
+                       "parallelism": parallelism_desc(world), "l2": "inputs (>1.7 GB of latents per step) are larger than L2",
                        "path": "umma" if lib.load().aero_has_umma() and dt == torch.bfloat16 else "simt",
                        "launch": "one CUDA graph replay per step" if graphed else "eager launches"},
             "clocks": clocks, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e}

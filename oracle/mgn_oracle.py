@@ -28,13 +28,14 @@ SD = Dict[str, torch.Tensor]
 # ---- torch_scatter 2.x semantics (call sites mgnLayer.py:144,146; bsms_mgn.py:265-283) ----------
 def scatter_add(src: torch.Tensor, index: torch.Tensor, dim_size: Optional[int] = None) -> torch.Tensor:
     n = int(index.max()) + 1 if dim_size is None else dim_size
-    out = torch.zeros((n,) + tuple(src.shape[1:]), dtype=src.dtype)
+    out = torch.zeros((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
     return out.index_add_(0, index, src)      # CPU: sequential in index order == scatter_add_
 
 
 def scatter_mean(src: torch.Tensor, index: torch.Tensor, dim_size: Optional[int] = None) -> torch.Tensor:
     s = scatter_add(src, index, dim_size)
-    cnt = torch.zeros(s.shape[0], dtype=src.dtype).index_add_(0, index, torch.ones(index.numel(), dtype=src.dtype))
+    cnt = torch.zeros(s.shape[0], dtype=src.dtype, device=src.device).index_add_(
+        0, index, torch.ones(index.numel(), dtype=src.dtype, device=src.device))
     return s / cnt.clamp(min=1).view(-1, *([1] * (src.dim() - 1)))
 
 
@@ -115,7 +116,7 @@ def mgn_forward(sd: SD, node_attr, edge_attr, edge_index, aggregation="add", act
 # ---- models/fouriermgn.py:111-183 ----------------------------------------------------------------
 def fourier_embedding(pos, dim=2, start=-3, length=7):
     xs = pos[:, :dim]
-    k = torch.arange(start, start + length, dtype=pos.dtype)
+    k = torch.arange(start, start + length, dtype=pos.dtype, device=pos.device)
     ph = ((2.0 ** k) * math.pi).view(1, 1, -1) * xs.unsqueeze(-1)
     return torch.cat([torch.cos(ph), torch.sin(ph)], dim=-1).reshape(pos.shape[0], -1)
 
@@ -130,7 +131,7 @@ def fourier_mgn_forward(sd: SD, node_attr, edge_attr, edge_index, aggregation="a
 def pool_mgn_forward(sd: SD, node_attr, edge_attr, edge_index, batch=None, method="mean", aggregation="add", act="relu"):
     g = mlp(sd, "global_encoder.", node_attr, act, use_ln=False)
     if batch is None:
-        batch = torch.zeros(node_attr.size(0), dtype=torch.long)
+        batch = torch.zeros(node_attr.size(0), dtype=torch.long, device=node_attr.device)
     nb = int(batch.max()) + 1
     if method == "mean":
         pooled = scatter_mean(g, batch, nb)
@@ -173,23 +174,27 @@ def coarsen_edge_indices(edge_index: np.ndarray, f2c: np.ndarray, nc: int):
 
 
 def downsample(x, e, edge_index, batch, pos, stride: int):
-    f2c_np, cb_np = stride_pool_indices(batch.numpy(), None if pos is None else pos[:, 0].numpy(), stride)
+    # integer part on the host in numpy (the bit-exact contract); tensors may live on any device (the tests run the
+    # same restatement in bf16 on the GPU as "the reference's own bf16 mode", train.py:30-33)
+    dev = x.device
+    f2c_np, cb_np = stride_pool_indices(batch.cpu().numpy(),
+                                        None if pos is None else pos[:, 0].float().cpu().numpy(), stride)
     nc = cb_np.shape[0]
-    f2c = torch.from_numpy(f2c_np)
+    f2c = torch.from_numpy(f2c_np).to(dev)
     cx = scatter_mean(x, f2c, nc)
     cpos = scatter_mean(pos, f2c, nc) if pos is not None else None
-    cei_np, inv_np = coarsen_edge_indices(edge_index.numpy(), f2c_np, nc)
+    cei_np, inv_np = coarsen_edge_indices(edge_index.cpu().numpy(), f2c_np, nc)
     if cei_np.shape[1] > 0:
-        ce = scatter_mean(e, torch.from_numpy(inv_np))
+        ce = scatter_mean(e, torch.from_numpy(inv_np).to(dev))
     else:
         ce = e.new_zeros((0, e.size(1)))
-    return cx, ce, torch.from_numpy(cei_np), torch.from_numpy(cb_np), cpos, f2c
+    return cx, ce, torch.from_numpy(cei_np).to(dev), torch.from_numpy(cb_np).to(dev), cpos, f2c
 
 
 # ---- models/bsms_mgn.py:126-215 --------------------------------------------------------------------
 def bsms_forward(sd: SD, node_attr, edge_attr, edge_index, batch=None, pos=None, stride=2, aggregation="add", act="relu"):
     if batch is None:
-        batch = torch.zeros(node_attr.size(0), dtype=torch.long)
+        batch = torch.zeros(node_attr.size(0), dtype=torch.long, device=node_attr.device)
     x = mlp(sd, "node_encoder.", node_attr, act)
     e = mlp(sd, "edge_encoder.", edge_attr, act)
     ei, b, p = edge_index, batch, pos
