@@ -435,7 +435,8 @@ int umma_block_fwd(const aero_block_desc* d, cudaStream_t st) {
   UmmaArgs a = make_uargs(d);
   if (d->agg) {
     a.agg_part = reinterpret_cast<float*>(d->workspace);
-    AERO_CUDA(cudaMemsetAsync(d->agg, 0, (size_t)d->n_nodes * 128 * sizeof(float), st));
+    if (!(d->flags & AERO_BLOCK_AGG_NO_CLEAR))
+      AERO_CUDA(cudaMemsetAsync(d->agg, 0, (size_t)d->n_nodes * 128 * sizeof(float), st));
   }
   if (d->rows == 0) return AERO_OK;
   // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute

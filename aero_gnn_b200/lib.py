@@ -13,6 +13,7 @@ LIB_PATH = PKG / "libaero_sm100.so"
 
 AERO_F32, AERO_BF16 = 0, 1
 AERO_PATH_SIMT, AERO_PATH_UMMA = 0, 1
+AERO_BLOCK_AGG_NO_CLEAR = 1
 ACT_CODES = {"relu": 0, "tanh": 1, "sigmoid": 2, "elu": 3, "leaky_relu": 4}
 
 c_i32p = C.POINTER(C.c_int32)
@@ -24,7 +25,7 @@ class BlockDesc(C.Structure):
 
     _fields_ = [
         ("dtype", C.c_int32), ("path", C.c_int32), ("L", C.c_int32), ("act", C.c_int32),
-        ("use_ln", C.c_int32), ("main_f32", C.c_int32), ("has_resid_grad", C.c_int32), ("reserved", C.c_int32),
+        ("use_ln", C.c_int32), ("main_f32", C.c_int32), ("has_resid_grad", C.c_int32), ("flags", C.c_int32),
         ("rows", C.c_int64), ("n_nodes", C.c_int64), ("ldp", C.c_int64), ("poff0", C.c_int64), ("poff1", C.c_int64),
         ("main", C.c_void_p), ("main_scale", C.c_void_p), ("resid", C.c_void_p), ("P", C.c_void_p),
         ("idx0", C.c_void_p), ("idx1", C.c_void_p), ("rowptr", C.c_void_p), ("prepared", C.c_void_p),

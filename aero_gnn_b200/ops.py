@@ -349,18 +349,54 @@ def _desc(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, main
 
 
 def block_fwd(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, main_scale=None, rowptr=None,
-              want_agg=False, kind=None, h0_out: Optional[torch.Tensor] = None):
+              want_agg=False, kind=None, h0_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+              agg_out: Optional[torch.Tensor] = None, agg_clear: bool = True, rows: Optional[tuple] = None):
     """Forward of one fused block; returns (out, agg or None).  `h0_out` ([rows,128], latent dtype, tcgen05 path
-    only) receives the first hidden activation so that the backward does not have to recompute it."""
+    only) receives the first hidden activation so that the backward does not have to recompute it.
+
+    `out` / `agg_out`: caller-provided result buffers (a stack writes x' straight into the next step's extended row
+    matrix; two launches over complementary row ranges share one aggregate).  `rows = (r0, r1)` runs the launch over
+    that sub-range of the rows only -- every per-row tensor (main, resid, idx0, idx1, main_scale, out, h0_out) is
+    addressed at row r0 + i, `rowptr` must then be the receiver CSR RELATIVE to r0 (rowptr - r0; r0 has to be a
+    segment boundary), and `agg_clear=False` keeps what an earlier launch put into `agg_out`."""
     _require_cuda(main, resid, P)
     lib = _l.load()
     n_nodes = P.size(0)
     d = _desc(prep, main, resid, P, idx0, idx1, poff0, poff1, main_scale=main_scale, rowptr=rowptr, n_nodes=n_nodes)
-    out = torch.empty((main.size(0), D), dtype=P.dtype, device=P.device)
-    agg = torch.empty((n_nodes, D), dtype=torch.float32, device=P.device) if want_agg else None
+    if out is None:
+        out = torch.empty((main.size(0), D), dtype=P.dtype, device=P.device)
+    elif out.shape != (main.size(0), D) or out.dtype != P.dtype or not out.is_contiguous():
+        raise RuntimeError("block_fwd: `out` must be a contiguous [rows, 128] tensor of the latent dtype")
+    if agg_out is not None:
+        if agg_out.shape != (n_nodes, D) or agg_out.dtype != torch.float32 or not agg_out.is_contiguous():
+            raise RuntimeError("block_fwd: `agg_out` must be a contiguous fp32 [n_nodes, 128] tensor")
+        agg = agg_out
+    else:
+        agg = torch.empty((n_nodes, D), dtype=torch.float32, device=P.device) if want_agg else None
     d.out = out.data_ptr()
     d.agg = agg.data_ptr() if agg is not None else None
     d.h0 = h0_out.data_ptr() if h0_out is not None else None
+    if not agg_clear:
+        d.flags = _l.AERO_BLOCK_AGG_NO_CLEAR
+    if rows is not None:
+        r0, r1 = int(rows[0]), int(rows[1])
+        if not (0 <= r0 <= r1 <= main.size(0)):
+            raise RuntimeError("block_fwd: bad row range")
+        if idx0 is None:
+            raise RuntimeError("block_fwd: a row range needs explicit gather indices (identity is relative to r0)")
+        d.rows = r1 - r0
+        d.main = main.data_ptr() + r0 * D * main.element_size()
+        d.out = out.data_ptr() + r0 * D * out.element_size()
+        if resid is not None:
+            d.resid = resid.data_ptr() + r0 * D * resid.element_size()
+        if main_scale is not None:
+            d.main_scale = main_scale.data_ptr() + r0 * 4
+        if idx0 is not None:
+            d.idx0 = idx0.data_ptr() + r0 * 4
+        if idx1 is not None:
+            d.idx1 = idx1.data_ptr() + r0 * 4
+        if h0_out is not None:
+            d.h0 = h0_out.data_ptr() + r0 * D * h0_out.element_size()
     ws = _workspace(lib.aero_block_workspace_bytes(C.byref(d), 0), P.device)
     d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
     tok = PROFILE.begin(kind)
@@ -382,7 +418,7 @@ def wgrad_into(g_w: torch.Tensor, g_h0: torch.Tensor, rows_in: torch.Tensor) -> 
 def block_bwd(prep: PreparedBlock, main, P, idx0, idx1, poff0, poff1, g_out, *, g_agg=None, main_scale=None,
               has_resid_grad=False, g_main_out: Optional[torch.Tensor] = None, kind=None,
               h0: Optional[torch.Tensor] = None, n_nodes: Optional[int] = None,
-              rowptr: Optional[torch.Tensor] = None):
+              rowptr: Optional[torch.Tensor] = None, g_w_out: Optional[torch.Tensor] = None):
     """Backward of one fused block; returns (g_main, g_h0, g_w_packed[fp32], W_main slot zero).  With `h0` (the
     rows kept by block_fwd(h0_out=...)) layer 0 is not recomputed and `P` may be None.  `rowptr` (receiver CSR of
     the rows, with `g_agg`) lets the TMA-fed kernel take d(beta)'s receiver part as sum_n deg(n) g_agg[n]."""
@@ -403,7 +439,13 @@ def block_bwd(prep: PreparedBlock, main, P, idx0, idx1, poff0, poff1, g_out, *, 
     rows = main.size(0)
     g_main = g_main_out if g_main_out is not None else torch.empty((rows, D), dtype=main.dtype, device=dev)
     g_h0 = torch.empty((rows, D), dtype=ldt, device=dev)
-    g_w = torch.zeros(packed_floats(prep.L), dtype=torch.float32, device=dev)
+    # every slot except W_main is written by the kernel (W_main: by the caller's wgrad_into); `g_w_out` lets a
+    # stack place the packed gradient inside one flat buffer (one all-reduce, no per-parameter copies)
+    if g_w_out is not None:
+        assert g_w_out.dtype == torch.float32 and g_w_out.numel() == packed_floats(prep.L) and g_w_out.is_contiguous()
+        g_w = g_w_out
+    else:
+        g_w = torch.zeros(packed_floats(prep.L), dtype=torch.float32, device=dev)
     d.has_resid_grad = int(has_resid_grad)
     d.g_out = g_out.data_ptr()
     d.g_agg = g_agg.data_ptr() if g_agg is not None else None

@@ -219,6 +219,47 @@ def cached_pack_step(module: torch.nn.Module, dtype: torch.dtype, build) -> Step
     return apply_pack_spec(spec)
 
 
+class GradSink:
+    """Flat fp32 buffer for the parameter gradients of a K-step stack:
+        [ (w_edge | w_node) x K | (w_proj [3D, D] | b_proj [3D]) x K ]
+    The block kernels and the weight-gradient GEMMs write their results straight into its slices, a partitioned mesh
+    sums it across ranks with ONE all-reduce, and the projection part is converted to the latent dtype with one
+    launch for all steps (instead of ~25 small cast / cat / copy launches per step)."""
+
+    def __init__(self, K: int, L_edge: int, L_node: int, device):
+        self.K, self.pe, self.pn = K, ops.packed_floats(L_edge), ops.packed_floats(L_node)
+        self.blk = self.pe + self.pn
+        self.pp = 3 * D * D + 3 * D
+        self.flat = torch.empty(K * (self.blk + self.pp), dtype=torch.float32, device=device)
+        self.proj = self.flat[K * self.blk:].view(K, self.pp)
+
+    def w_edge(self, k: int) -> torch.Tensor:
+        return self.flat[k * self.blk: k * self.blk + self.pe]
+
+    def w_node(self, k: int) -> torch.Tensor:
+        return self.flat[k * self.blk + self.pe: (k + 1) * self.blk]
+
+    def w_proj(self, k: int) -> torch.Tensor:
+        return self.proj[k, : 3 * D * D].view(3 * D, D)
+
+    def finish(self, dtype: torch.dtype, reduce=None):
+        """Fill the b_proj slots (= column sums of g_h0, kept by the block kernels in their packed bias0 slot), sum
+        across ranks when `reduce` is given, and return per step (g_w_edge, g_w_node, g_w_proj, g_b_proj)."""
+        K = self.K
+        blocks = self.flat[: K * self.blk].view(K, self.blk)
+        b0e = blocks[:, self.pe - D: self.pe]                  # bias0 slot = last D floats of a packed block
+        b0n = blocks[:, self.blk - D:]
+        bp = self.proj[:, 3 * D * D:].view(K, 3, D)
+        bp[:, 0].copy_(b0e)      # gradient of the (zero) sender-part bias: same column sums, unused by the caller
+        bp[:, 1].copy_(b0e)
+        bp[:, 2].copy_(b0n)
+        if reduce is not None:
+            reduce(self.flat)
+        proj = self.proj if dtype == torch.float32 else self.proj.to(dtype)
+        return [(self.w_edge(k), self.w_node(k), proj[k, : 3 * D * D].view(3 * D, D), proj[k, 3 * D * D:])
+                for k in range(K)]
+
+
 class MGNStackFn(torch.autograd.Function):
     """apply(cfg, plan, x, e_csr, *flat) with flat = (w_edge, w_node, w_proj, b_proj) per step."""
 
@@ -277,7 +318,7 @@ class MGNStackFn(torch.autograd.Function):
         # G_e is updated in place layer by layer; the edge output is usually unused (no gradient materialised)
         G_e = torch.zeros_like(acts[1]) if G_e is None else G_e.contiguous().to(dt).clone()
         scale = plan.inv_deg if cfg.mean else None
-        grads: List[Optional[torch.Tensor]] = [None] * (4 * K)
+        sink = GradSink(K, cfg.L_edge, cfg.L_node, acts[0].device)
         for k in reversed(range(K)):
             x, e, agg, a1, a2 = acts[5 * k: 5 * k + 5]
             P, h0e, h0n = (None, a1, a2) if ctx.keep_h0 else (a1, None, None)
@@ -289,13 +330,13 @@ class MGNStackFn(torch.autograd.Function):
                 pn = ops.PreparedBlock(w_node, cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
             # node block: g_agg, gradient of the node pre-activation, MLP weight grads
             g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale,
-                                               kind="node_bwd", h0=h0n, n_nodes=plan.N)
+                                               kind="node_bwd", h0=h0n, n_nodes=plan.N, g_w_out=sink.w_node(k))
             agg_eff = agg if scale is None else agg * scale[:, None]
             ops.wgrad_into(g_wn, g_h0n, agg_eff.to(dt))
             # edge block: total gradient of e' = G_e + g_agg[receiver]
             G_e, g_h0e, g_we = ops.block_bwd(pe, e, P, plan.src, plan.dst, 0, D, G_e, g_agg=g_agg,
                                              has_resid_grad=True, g_main_out=G_e, kind="edge_bwd", h0=h0e,
-                                             n_nodes=plan.N, rowptr=plan.rowptr)
+                                             n_nodes=plan.N, rowptr=plan.rowptr, g_w_out=sink.w_edge(k))
             ops.wgrad_into(g_we, g_h0e, e)
             # gradients of the gathered projections: segmented sums by sender and by receiver
             # (both land in one [N, 2D] matrix, so the products with W_s | W_d are single K = 2D GEMMs)
@@ -304,13 +345,13 @@ class MGNStackFn(torch.autograd.Function):
             ops.segment_reduce(g_h0e, plan.rowptr, None, plan.N, out=g_psd[:, D:])
             g_x = torch.addmm(G_x, g_psd, w_proj[:2 * D])
             g_x.addmm_(g_h0n, w_proj[2 * D:])
-            g_wproj = torch.empty_like(w_proj)
-            torch.mm(g_psd.t(), x, out=g_wproj[:2 * D])
-            torch.mm(g_h0n.t(), x, out=g_wproj[2 * D:])
-            # column sums of g_h0 come out of the block kernels (fp32): sum over edges == sum over senders == receivers
-            g_bproj = torch.cat([g_we[-D:], g_we[-D:], g_wn[-D:]])
-            grads[4 * k: 4 * k + 4] = [g_we, g_wn, g_wproj.to(w_proj.dtype), g_bproj.to(b_proj.dtype)]
+            g_wproj = sink.w_proj(k)                 # fp32, written by the GEMMs
+            torch.mm(g_psd.t(), x, out_dtype=torch.float32, out=g_wproj[:2 * D])
+            torch.mm(g_h0n.t(), x, out_dtype=torch.float32, out=g_wproj[2 * D:])
             G_x = g_x
+        grads: List[Optional[torch.Tensor]] = []
+        for per_step in sink.finish(flat[2].dtype):
+            grads += list(per_step)
         return (None, None, G_x, G_e, *grads)
 
 

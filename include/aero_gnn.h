@@ -166,6 +166,8 @@ int aero_multi_copy(const aero_copy_seg* segs, int n_segs, void* stream);
  * all matrices in nn.Linear layout [out][in].  aero_block_prepare turns them into the image
  * the chosen path reads (SIMT: fp32 + transposes; UMMA: bf16 swizzled shared-memory images).
  * ------------------------------------------------------------------------------------------ */
+#define AERO_BLOCK_AGG_NO_CLEAR 1
+
 typedef struct aero_block_desc {
   int32_t dtype;      /* AERO_F32 | AERO_BF16: storage of main/resid/out/P/g_* rows            */
   int32_t path;       /* AERO_PATH_SIMT | AERO_PATH_UMMA                                       */
@@ -175,7 +177,9 @@ typedef struct aero_block_desc {
   int32_t main_f32;   /* 1: `main` (and g_main) rows are fp32 regardless of dtype (node block:
                          main = fp32 aggregate)                                                */
   int32_t has_resid_grad; /* bwd: 1 -> g_main = g_out + g_h0 @ W_main (edge: resid == main)    */
-  int32_t reserved;
+  int32_t flags;      /* AERO_BLOCK_*: bit 0 = forward does not clear `agg` first (a launch over a sub-range of
+                         the rows of one mesh, e.g. boundary edges after the halo arrived, adds its receivers
+                         to an aggregate an earlier launch over the other rows already started)               */
   int64_t rows;       /* E or N                                                                */
   int64_t n_nodes;    /* N (rows of P, agg)                                                    */
   int64_t ldp;        /* row stride of P in elements (384)                                     */

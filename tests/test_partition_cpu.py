@@ -22,33 +22,45 @@ def _free_port():
     return p
 
 
-def test_halo_plan_covers_every_edge_once():
+@pytest.mark.parametrize("reorder", [True, False])
+def test_halo_plan_covers_every_edge_once(reorder):
     mesh = airfoil_o_mesh(16, 9, seed=0)
     ei, n = mesh.edge_index.numpy(), mesh.num_nodes
-    for world in (1, 2, 3, 8):
+    for world in (1, 2, 3, 8, 200):          # 200 > number of nodes in some blocks: empty ranks
         seen = []
         for r in range(world):
-            pl = build_halo_plan(ei, n, r, world)
+            pl = build_halo_plan(ei, n, r, world, reorder=reorder)
             lo, hi = block_bounds(n, world, r)
             assert (pl.lo, pl.hi) == (lo, hi)
             g = ei[:, pl.edge_ids]
             assert np.all((g[1] >= lo) & (g[1] < hi))
-            # local ids map back to the global sender / receiver
-            table = np.concatenate([np.arange(lo, hi), pl.halo_global])
+            # local ids map back to the global sender / receiver; own rows are a permutation of the block
+            assert np.array_equal(np.sort(pl.own_order), np.arange(hi - lo))
+            table = np.concatenate([pl.own_order + lo, pl.halo_global])
             assert np.array_equal(table[pl.local_edge_index[0]], g[0])
-            assert np.array_equal(pl.local_edge_index[1] + lo, g[1])
+            assert np.array_equal(table[pl.local_edge_index[1]], g[1])
+            # interior receivers (local rows < n_interior) have owned senders only; boundary receivers at least one remote
+            recv_l, send_l = pl.local_edge_index[1], pl.local_edge_index[0]
+            assert np.all(send_l[recv_l < pl.n_interior] < pl.n_own)
+            if reorder:
+                has_remote = np.zeros(pl.n_own, dtype=bool)
+                has_remote[recv_l[send_l >= pl.n_own]] = True
+                assert np.array_equal(has_remote, np.arange(pl.n_own) >= pl.n_interior)
+                assert np.all(np.diff(pl.own_order[:pl.n_interior]) > 0) and np.all(np.diff(pl.own_order[pl.n_interior:]) > 0)
+            else:
+                assert pl.n_interior == 0 and np.array_equal(pl.own_order, np.arange(pl.n_own))
             assert np.all((pl.halo_global < lo) | (pl.halo_global >= hi)) and np.all(np.diff(pl.halo_global) > 0)
             assert sum(pl.recv_counts) == pl.n_halo
             seen.append(pl.edge_ids)
         assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(ei.shape[1]))
         # what r sends to p is exactly what p expects from r
-        plans = [build_halo_plan(ei, n, r, world) for r in range(world)]
+        plans = [build_halo_plan(ei, n, r, world, reorder=reorder) for r in range(world)]
         for r in range(world):
             for p in range(world):
                 if r != p:
                     plo, phi = block_bounds(n, world, r)
                     want = plans[p].halo_global[(plans[p].halo_global >= plo) & (plans[p].halo_global < phi)]
-                    assert np.array_equal(plans[r].send_idx[p] + plo, want)
+                    assert np.array_equal(plans[r].own_order[plans[r].send_idx[p]] + plo, want)
 
 
 def _worker(rank, world, port, ei, n, out):
@@ -58,22 +70,25 @@ def _worker(rank, world, port, ei, n, out):
         pl = build_halo_plan(ei, n, rank, world)
         ex = HaloExchanger(pl, "cpu")
         xg = torch.arange(n, dtype=torch.float32)[:, None] * torch.ones(1, 4) + torch.arange(4) * 0.25
-        halo = ex.forward(xg[pl.lo:pl.hi].contiguous())
+        own = torch.from_numpy(pl.own_order)                         # local row i = global own row own[i]
+        x_loc = xg[pl.lo:pl.hi][own].contiguous()
+        halo = ex.forward(x_loc)
         ok_f = torch.equal(halo, xg[torch.from_numpy(pl.halo_global)])
         # reverse: every rank returns (rank+1) * ones for each of its halo rows
         g_own = torch.zeros(pl.n_own, 4)
         ex.backward(torch.full((pl.n_halo, 4), float(rank + 1)), g_own)
-        expect = torch.zeros(pl.n_own, 4)
+        expect_g = torch.zeros(pl.n_own, 4)                          # in global own order
         for p in range(world):
             if p != rank:
                 other = build_halo_plan(ei, n, p, world)
                 ids = other.halo_global[(other.halo_global >= pl.lo) & (other.halo_global < pl.hi)] - pl.lo
-                expect[torch.from_numpy(ids)] += float(p + 1)
+                expect_g[torch.from_numpy(ids)] += float(p + 1)
+        expect = expect_g[own]
         ok_b = torch.equal(g_own, expect)
         # split-phase form: post, do unrelated work, finish; receive straight into a slice of a larger buffer
         x_ext = torch.full((pl.n_local, 4), -1.0)
-        tok = ex.forward_start(xg[pl.lo:pl.hi].contiguous(), out=x_ext[pl.n_own:])
-        x_ext[:pl.n_own] = xg[pl.lo:pl.hi]
+        x_ext[:pl.n_own] = x_loc
+        tok = ex.forward_start(x_ext, out=x_ext[pl.n_own:])
         ex.forward_finish(tok)
         ok_f = ok_f and torch.equal(x_ext[pl.n_own:], xg[torch.from_numpy(pl.halo_global)])
         g2 = torch.zeros(pl.n_own, 4)
