@@ -18,7 +18,7 @@ BUILD = PKG / "build"
 LIB = PKG / "libaero_sm100.so"
 
 SOURCES = ["abi.cu", "sort_plan.cu", "segment.cu", "block_simt.cu", "block_umma.cu", "block_umma_bwd.cu", "block_umma_bwd2.cu",
-           "umma_probe.cu", "bistride.cu"]
+           "umma_probe.cu", "bistride.cu", "train_tail.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

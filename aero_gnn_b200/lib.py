@@ -57,6 +57,13 @@ class CopySeg(C.Structure):
                 ("src_ld", C.c_int64), ("dst_ld", C.c_int64), ("src_dtype", C.c_int32), ("dst_dtype", C.c_int32)]
 
 
+class AdamSeg(C.Structure):
+    """Mirror of struct aero_adam_seg (include/aero_gnn.h)."""
+
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("master", C.c_void_p),
+                ("n", C.c_int64), ("p_dtype", C.c_int32), ("g_dtype", C.c_int32)]
+
+
 MAX_COPY_SEGS = 48
 
 # name -> (restype, argtypes); every symbol declared in include/aero_gnn.h
@@ -99,6 +106,11 @@ SIGNATURES = {
     "aero_filter_edges": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64] + [C.c_void_p] * 3
                           + [C.c_void_p, C.c_size_t, C.c_void_p]),
     "aero_multi_copy": (C.c_int, [C.POINTER(CopySeg), C.c_int, C.c_void_p]),
+    "aero_mse_workspace_bytes": (C.c_size_t, []),
+    "aero_mse_loss_grad": (C.c_int, [C.c_void_p] * 4 + [C.c_int64] * 4 + [C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_size_t,
+                                      C.c_void_p]),
+    "aero_adam_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                 C.c_int64, C.c_void_p]),
     "aero_wec_workspace_bytes": (C.c_size_t, [C.POINTER(WecDesc), C.c_int]),
     "aero_wec_fwd": (C.c_int, [C.POINTER(WecDesc), C.c_void_p]),
     "aero_wec_bwd": (C.c_int, [C.POINTER(WecDesc), C.c_void_p]),

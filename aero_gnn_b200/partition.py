@@ -4,7 +4,8 @@ The reference has no distributed code; this is new.  Rank r owns
 whose receiver it owns, so edge latents, the edge block and the receiver sums stay local and deterministic.  A
 processor step reads only 1-hop sender latents (mgnLayer.py:40-41), so the only data crossing ranks is the latent
 row of each remote sender ("halo"), once per step forward and the gradient of those rows once per step backward.
-Weights are replicated; their gradients are summed with ONE all-reduce of a flat buffer after the backward pass.
+Weights are replicated; their gradients are summed by all-reduces of flat fp32 buckets (5 steps each) that travel
+under the backward of the earlier steps.
 
 Local numbering.  Own nodes first, halo nodes (ascending global id) after them.  Inside the own block the
 INTERIOR receivers -- own nodes all of whose incoming edges have an owned sender -- come first and the BOUNDARY
@@ -272,7 +273,9 @@ class PartitionedStackFn(torch.autograd.Function):
         G_x = torch.zeros_like(acts[0][:n_own]) if G_x is None else G_x.contiguous().to(dt)
         G_e = torch.zeros_like(acts[1]) if G_e is None else G_e.contiguous().to(dt).clone()
         scale = part.inv_deg_own if cfg.mean else None
-        sink = GradSink(K, cfg.L_edge, cfg.L_node, acts[0].device)
+        # parameter gradients: flat fp32 buckets, summed over the ranks while earlier steps are still in their backward
+        reduce = (lambda t: dist.all_reduce(t, group=part.group, async_op=True)) if part.world > 1 else None
+        sink = GradSink(K, cfg.L_edge, cfg.L_node, acts[0].device, reduce=reduce)
         for k in reversed(range(K)):
             x_ext, e, agg, a1, a2 = acts[5 * k: 5 * k + 5]
             P, h0e, h0n = (None, a1, a2) if ctx.keep_h0 else (a1, None, None)
@@ -302,11 +305,10 @@ class PartitionedStackFn(torch.autograd.Function):
             torch.mm(g_psd.t(), x_ext, out_dtype=torch.float32, out=g_wproj[:2 * D])
             torch.mm(g_h0n.t(), x, out_dtype=torch.float32, out=g_wproj[2 * D:])
             ex.backward_finish(tok, g_x)
+            sink.step_done(k)
             G_x = g_x
-        # one all-reduce of every parameter gradient of the stack (fp32 sums of the per-rank partials)
-        reduce = (lambda t: dist.all_reduce(t, group=part.group)) if part.world > 1 else None
         grads = []
-        for per_step in sink.finish(flat[2].dtype, reduce):
+        for per_step in sink.finish(flat[2].dtype):
             grads += list(per_step)
         return (None, None, G_x, G_e, *grads)
 

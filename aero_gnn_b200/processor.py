@@ -219,45 +219,77 @@ def cached_pack_step(module: torch.nn.Module, dtype: torch.dtype, build) -> Step
     return apply_pack_spec(spec)
 
 
-class GradSink:
-    """Flat fp32 buffer for the parameter gradients of a K-step stack:
-        [ (w_edge | w_node) x K | (w_proj [3D, D] | b_proj [3D]) x K ]
-    The block kernels and the weight-gradient GEMMs write their results straight into its slices, a partitioned mesh
-    sums it across ranks with ONE all-reduce, and the projection part is converted to the latent dtype with one
-    launch for all steps (instead of ~25 small cast / cat / copy launches per step)."""
+# Cross-rank reduction of the stack's parameter gradients (data-parallel training of batched small meshes,
+# train.py:50-51; the receiver-block partition passes its own).  `fn(flat_fp32_span) -> work | None` starts an
+# all-reduce (async_op=True returns a work handle that is waited for before the gradients are handed to autograd);
+# it is called once per bucket of `bucket_layers` processor steps, as soon as the backward has produced them, so
+# the reduction of step k's gradients travels under the backward kernels of steps < k.
+_GRAD_REDUCE = {"fn": None, "bucket_layers": 5}
 
-    def __init__(self, K: int, L_edge: int, L_node: int, device):
+
+def set_grad_reduce(fn, bucket_layers: int = 5) -> None:
+    _GRAD_REDUCE["fn"], _GRAD_REDUCE["bucket_layers"] = fn, max(int(bucket_layers), 1)
+
+
+class GradSink:
+    """Flat fp32 buffer for the parameter gradients of a K-step stack, per step contiguous:
+        [ w_edge | w_node | w_proj [3D, D] | b_proj [3D] ] x K
+    The block kernels and the weight-gradient GEMMs write their results straight into its slices; a bucket of steps
+    is summed across ranks with ONE all-reduce of one contiguous span while earlier steps are still in their backward;
+    the projection parts are converted to the latent dtype with one launch for all steps (instead of ~25 small cast /
+    cat / copy launches per step)."""
+
+    def __init__(self, K: int, L_edge: int, L_node: int, device, reduce=None, bucket_layers: Optional[int] = None):
         self.K, self.pe, self.pn = K, ops.packed_floats(L_edge), ops.packed_floats(L_node)
         self.blk = self.pe + self.pn
         self.pp = 3 * D * D + 3 * D
-        self.flat = torch.empty(K * (self.blk + self.pp), dtype=torch.float32, device=device)
-        self.proj = self.flat[K * self.blk:].view(K, self.pp)
+        self.per = self.blk + self.pp
+        self.flat = torch.empty(K * self.per, dtype=torch.float32, device=device)
+        self.rows = self.flat.view(K, self.per)
+        self.reduce = reduce if reduce is not None else _GRAD_REDUCE["fn"]
+        self.bucket = max(int(bucket_layers or _GRAD_REDUCE["bucket_layers"]), 1)
+        self.works, self.hi = [], K          # steps [hi, K) have been handed to the reduction
 
     def w_edge(self, k: int) -> torch.Tensor:
-        return self.flat[k * self.blk: k * self.blk + self.pe]
+        return self.rows[k, : self.pe]
 
     def w_node(self, k: int) -> torch.Tensor:
-        return self.flat[k * self.blk + self.pe: (k + 1) * self.blk]
+        return self.rows[k, self.pe: self.blk]
 
     def w_proj(self, k: int) -> torch.Tensor:
-        return self.proj[k, : 3 * D * D].view(3 * D, D)
+        return self.rows[k, self.blk: self.blk + 3 * D * D].view(3 * D, D)
 
-    def finish(self, dtype: torch.dtype, reduce=None):
-        """Fill the b_proj slots (= column sums of g_h0, kept by the block kernels in their packed bias0 slot), sum
-        across ranks when `reduce` is given, and return per step (g_w_edge, g_w_node, g_w_proj, g_b_proj)."""
-        K = self.K
-        blocks = self.flat[: K * self.blk].view(K, self.blk)
-        b0e = blocks[:, self.pe - D: self.pe]                  # bias0 slot = last D floats of a packed block
-        b0n = blocks[:, self.blk - D:]
-        bp = self.proj[:, 3 * D * D:].view(K, 3, D)
+    def _flush(self, lo: int) -> None:
+        """Steps [lo, hi) are complete: fill their b_proj slots (= column sums of g_h0, which the block kernels leave
+        in the bias0 slot of their packed gradient) and start their cross-rank sum."""
+        r = self.rows[lo: self.hi]
+        bp = r[:, self.blk + 3 * D * D:].view(-1, 3, D)
+        b0e, b0n = r[:, self.pe - D: self.pe], r[:, self.blk - D: self.blk]
         bp[:, 0].copy_(b0e)      # gradient of the (zero) sender-part bias: same column sums, unused by the caller
         bp[:, 1].copy_(b0e)
         bp[:, 2].copy_(b0n)
-        if reduce is not None:
-            reduce(self.flat)
-        proj = self.proj if dtype == torch.float32 else self.proj.to(dtype)
+        if self.reduce is not None:
+            w = self.reduce(self.flat[lo * self.per: self.hi * self.per])
+            if w is not None:
+                self.works.append(w)
+        self.hi = lo
+
+    def step_done(self, k: int) -> None:
+        """The backward has written every gradient of step k (steps complete in descending order)."""
+        if self.reduce is not None and self.hi - k >= self.bucket:
+            self._flush(k)
+
+    def finish(self, dtype: torch.dtype):
+        """-> per step (g_w_edge, g_w_node, g_w_proj, g_b_proj); waits for the outstanding reductions."""
+        if self.hi > 0:
+            self._flush(0)
+        for w in self.works:
+            w.wait()
+        proj = self.rows[:, self.blk:]
+        if dtype != torch.float32:
+            proj = proj.to(dtype)
         return [(self.w_edge(k), self.w_node(k), proj[k, : 3 * D * D].view(3 * D, D), proj[k, 3 * D * D:])
-                for k in range(K)]
+                for k in range(self.K)]
 
 
 class MGNStackFn(torch.autograd.Function):
@@ -348,6 +380,7 @@ class MGNStackFn(torch.autograd.Function):
             g_wproj = sink.w_proj(k)                 # fp32, written by the GEMMs
             torch.mm(g_psd.t(), x, out_dtype=torch.float32, out=g_wproj[:2 * D])
             torch.mm(g_h0n.t(), x, out_dtype=torch.float32, out=g_wproj[2 * D:])
+            sink.step_done(k)
             G_x = g_x
         grads: List[Optional[torch.Tensor]] = []
         for per_step in sink.finish(flat[2].dtype):

@@ -1,14 +1,21 @@
-"""bench.py -- MGN-15 processor edges/sec (fwd+bwd) on the synthetic 1M-node / 5.996M-edge wing mesh.
+"""bench.py -- MGN-15 processor edges/sec (fwd+bwd) on the synthetic 1M-node / 5.996M-edge wing mesh (C5), plus
+the other BASELINE.json configurations on request.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nu 1000 --nv 1000]
-  torchrun ... bench.py --gpus N ...            (one rank per GPU, NCCL; the mesh is partitioned by
-                                                 contiguous receiver-node blocks with a halo exchange per step)
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c5|c2|c3]
+  torchrun ... bench.py --gpus N ...            (one rank per GPU, NCCL)
 
-One "step" = one forward + backward of the 15-step MeshGraphNets processor over the whole mesh
-(models/mgn.py:127-128 of the reference; encoders / decoder / loss / optimizer are outside the processor metric).
-`value` = edges / second with the latent inputs resident in HBM; `e2e` = the same metric through the public
-nn.Module API (MeshGraphNet.forward + MSE loss + backward) with the raw features copied from pinned host memory
-and the loss read back every step.  Prints ONE JSON line on rank 0.
+--config c5 (default; the configuration BASELINE.json's metric is quoted on).  One "step" = one forward + backward of
+  the 15-step MeshGraphNets processor over the whole mesh (models/mgn.py:127-128 of the reference; encoders / decoder
+  / loss / optimizer are outside the processor metric).  N > 1: the mesh is partitioned by contiguous receiver-node
+  blocks with one halo exchange per step (strong scaling).  `value` = edges / second with the latent inputs resident
+  in HBM, the step replayed as ONE CUDA graph at every N; `e2e` = the same metric through the public nn.Module API
+  (encoders + processor + decoder + MSE loss + backward) with the raw features copied from pinned host memory and the
+  loss read back every step.
+--config c2: whole training step (model forward, fused MSE, backward, gradient all-reduce, fused Adam) on a batch of
+  8 synthetic 5k-node airfoil meshes per rank, bf16, data-parallel over N ranks (weak scaling), value = edges / s.
+--config c3: BiStridedMeshGraphNet (4 levels, stride 2) forward + backward on the 100k-node airfoil mesh; N > 1 runs
+  N independent replicas (the bistride hierarchy is not partitioned).
+Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -33,6 +40,7 @@ CFG = dict(processor_size=15, activation_fn="relu", num_hidden_layers_node_proce
            hidden_dim_node_encoder=128, num_hidden_layers_edge_encoder=2, hidden_dim_edge_encoder=128,
            aggregation="add", hidden_dim_decoder=128, num_hidden_layers_decoder=2, dropout=0.0,
            do_concat_trick=True)   # config.yaml:40-51
+METRIC = "MGN-15 processor edges/sec (fwd+bwd)"
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -106,6 +114,46 @@ def kernel_alg_flops(kind, E, N, L=2):
     rows = E if kind.startswith("edge") else N
     per_row = 2 * D * D * (L + 2)
     return rows * per_row * (2 if kind.endswith("bwd") else 1)
+
+
+TRAFFIC_SOURCES = ["aero_gnn_b200/csrc/block_umma.cu", "aero_gnn_b200/csrc/block_umma_bwd.cu",
+                   "aero_gnn_b200/csrc/block_umma_bwd2.cu", "aero_gnn_b200/csrc/umma_block.cuh",
+                   "aero_gnn_b200/csrc/umma.cuh", "aero_gnn_b200/csrc/tma.cuh"]
+
+
+def sources_sha256(files=TRAFFIC_SOURCES):
+    import hashlib
+    h = hashlib.sha256()
+    for f in files:
+        h.update(open(os.path.join(ROOT, f), "rb").read())
+    return h.hexdigest()
+
+
+def ncu_traffic(kind, N, E, dtype):
+    """DRAM bytes per launch of a fused kernel from the newest committed `ncu --set full` capture of the same workload
+    (profiles/rNN_ncu_traffic.json, written by scripts/ncu_traffic.py).  The file names the commit and the sha256 of the
+    kernel sources it was captured at; a capture whose sources differ from the tree is STALE and is not reported
+    (traffic = null, the reason in traffic_capture)."""
+    import glob
+    best = None
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json"))):
+        try:
+            tj = json.load(open(p))
+        except Exception:
+            continue
+        if tj.get("workload") == {"N": N, "E": E, "dtype": dtype} and kind in tj:
+            best = tj
+    if best is None:
+        return None, None
+    if not best.get("sources_sha256"):
+        return None, "stale: capture carries no source stamp"
+    try:
+        now = sources_sha256(best.get("sources", TRAFFIC_SOURCES))
+    except OSError:
+        return None, "stale: a stamped source file is missing"
+    if now != best["sources_sha256"]:
+        return None, f"stale: captured at {best.get('commit', '?')}, kernel sources changed since"
+    return best[kind]["read_bytes"] + best[kind]["write_bytes"], f"ncu --set full at {best.get('commit', '?')}"
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -197,9 +245,23 @@ def cpu_arm(steps, warmup, budget_s, threads):
             "ms_min": min(ts) * 1e3, "ms_max": max(ts) * 1e3, "full_mesh": nv == 1000}
 
 
-def workload_desc(N, E):
+def workload_desc(config, N, E):
+    if config == "c2":
+        return (f"C2: MGN (15 steps) training step on a batch of 8 synthetic 5k-node airfoil meshes per rank "
+                f"(N={N} E={E} per rank): forward, MSE loss, backward, gradient all-reduce, Adam; latent 128, L=2, "
+                f"sum-trick edge block, aggregation add")
+    if config == "c3":
+        return (f"C3: BiStridedMeshGraphNet (4 levels, 2 layers per scale, stride 2) forward + MSE + backward on the "
+                f"synthetic 100k-node airfoil mesh (N={N} E={E}); latent 128, L=2")
     return (f"MGN-15 processor fwd+bwd on the synthetic 3-D wing surface mesh (C5): N={N} E={E}, latent 128, L=2, "
             f"sum-trick edge block, aggregation add")
+
+
+def parallelism_desc(config, world):
+    if world == 1:
+        return "single"
+    return {"c5": f"receiver-block partition x{world} + halo exchange", "c2": f"dp{world}",
+            "c3": f"{world} independent replicas"}[config]
 
 
 def run_reference(args, rank, world):
@@ -208,10 +270,10 @@ def run_reference(args, rank, world):
     threads = os.cpu_count() or 1
     r = cpu_arm(args.steps, args.warmup, 150.0, threads)
     N, E = args.nu * args.nv, 2 * args.nu * (3 * args.nv - 2)
-    line = {"impl": "reference", "metric": "MGN-15 processor edges/sec (fwd+bwd)", "value": r["value"], "unit": "edges/s",
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "edges/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_desc(N, E), "parallelism": parallelism_desc(world)},
+            "config": {"workload": workload_desc("c5", N, E), "parallelism": parallelism_desc("c5", world)},
             "cpu_baseline": {"value": r["value"], "unit": "edges/s", "cores": threads, "kind": r["kind"],
                              "sample": r["sample"], "step_ms_min_max": [r["ms_min"], r["ms_max"]]},
             "e2e": {"value": r["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -219,53 +281,141 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def parallelism_desc(world):
-    return "single" if world == 1 else f"receiver-block partition x{world} + halo exchange"
+# ---------------------------------------------------------------------------------------------------
+class Timer:
+    """W untimed steps, then K steps between CUDA events on the launching stream, barrier + synchronize on both sides,
+    max over ranks."""
+
+    def __init__(self, dev, world, rank):
+        self.dev, self.world, self.rank = dev, world, rank
+
+    def sync(self):
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def run(self, step, steps, warmup=0):
+        import torch.distributed as dist
+        for _ in range(warmup):
+            step()
+        self.sync()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            step()
+        ev1.record()
+        self.sync()
+        ms = ev0.elapsed_time(ev1) / max(steps, 1)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+
+def graphed(step, world, dev, rank, want):
+    """-> (callable, is_graph): `step` recorded into one CUDA graph when wanted and possible on every rank."""
+    import torch.distributed as dist
+    from aero_gnn_b200 import ops
+    if not want:
+        return step, False
+    ok, g = True, None
+    try:
+        from aero_gnn_b200.graphs import GraphedStep
+        g = GraphedStep(step, warmup=1)
+        for _ in range(2):
+            g()
+    except Exception as exc:   # noqa: BLE001 -- report and time the eager step instead
+        print(f"[bench] CUDA-graph capture failed on rank {rank}: {exc!r}; timing the eager step", file=sys.stderr)
+        ok = False
+    if world > 1:   # every rank must time the same kind of step
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(int(flag.item()))
+    ops.PROFILE.reset(enabled=False)
+    return (g, True) if ok else (step, False)
+
+
+def shutdown(world, holder):
+    """Tear the process group down.  Captured graphs that contain NCCL kernels must be released first, and a watchdog
+    bounds the teardown: the result line is already printed, a wedged communicator must not hang the job."""
+    if world <= 1:
+        return
+    import gc
+    import torch.distributed as dist
+    dog = threading.Timer(45.0, lambda: os._exit(0))
+    dog.daemon = True
+    dog.start()
+    holder.clear()
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+    dog.cancel()
+
+
+def e2e_pipeline(host, dev, step_fn, steps, warmup):
+    """Times `step_fn(device buffers) -> device scalar loss` with the step's inputs copied from pinned host memory
+    inside the timed region (double buffered on a copy stream: the copy of step i+1 travels under step i; every step
+    still copies its own inputs) and the loss read back every step.  -> seconds per step (wall clock around a
+    synchronised region, which is what an end-to-end number is)."""
+    copy_stream = torch.cuda.Stream()
+    bufs = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    freed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def issue_copy(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[slot])          # the step that last read this buffer has finished
+            for d, h in zip(bufs[slot], host):
+                d.copy_(h, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def one(i):
+        slot = i & 1
+        torch.cuda.current_stream().wait_event(ready[slot])
+        issue_copy(slot ^ 1)                             # next step's inputs travel under this step's compute
+        loss = step_fn(bufs[slot])
+        freed[slot].record()
+        return float(loss.item())                        # device -> host read of the step's result
+
+    for ev in freed:
+        ev.record()
+    issue_copy(0)
+    for i in range(warmup):
+        one(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(warmup, warmup + steps):
+        one(i)
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / steps
 
 
 # ---------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nu", type=int, default=1000)
-    ap.add_argument("--nv", type=int, default=1000)
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay the processor step as one CUDA graph (auto: only when the mesh is partitioned)")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-
+def bench_c5(args, rank, world, local, dev):
     import torch.distributed as dist
     from aero_gnn_b200 import lib, ops
     import aero_gnn_b200.models as M
     from aero_gnn_b200.meshes import wing_surface_mesh
     from aero_gnn_b200.models._common import run_layers
+    from aero_gnn_b200.processor import permute_rows
+    from aero_gnn_b200.train_tail import mse_loss
 
-    lib.load()
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     dt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     b = 2 if dt == torch.bfloat16 else 4
-
     mesh = wing_surface_mesh(args.nu, args.nv)
     N, E = mesh.num_nodes, mesh.num_edges
     torch.manual_seed(0)
     net = M.MeshGraphNet(6, 4, 5, **CFG).to(dev).to(dt)
+    timer = Timer(dev, world, rank)
+    holder = {}
 
     # ---- device-resident processor benchmark ----------------------------------------------------
     g = torch.Generator().manual_seed(1234)
+    pp = None
     if world == 1:
         plan = ops.PLAN_CACHE.get(mesh.edge_index.to(dev), N)
         x0 = torch.randn(N, D, generator=g).to(dev, dt).requires_grad_(True)
@@ -282,203 +432,313 @@ def main():
         from aero_gnn_b200.partition import PartitionedProcessor
         pp = PartitionedProcessor(mesh.edge_index, N, rank, world, dev)
         x0 = torch.randn(N, D, generator=g)[pp.lo:pp.hi].to(dev, dt).requires_grad_(True)
-        e0 = torch.randn(E, D, generator=g)[pp.edge_ids_cpu].to(dev, dt).requires_grad_(True)
+        e0 = torch.randn(E, D, generator=g)[pp.csr_edge_ids().cpu()].to(dev, dt).requires_grad_(True)
         gx = torch.ones(pp.n_own, D, device=dev, dtype=dt)
 
         def proc_step():
             for p in net.layers.parameters():
                 p.grad = None
             x0.grad = e0.grad = None
-            x, e = pp.run(net.layers, x0, e0)
+            x, e = pp.run(net.layers, x0, e0)       # weight gradients are summed over the ranks inside the backward
             torch.autograd.backward([x], [gx])
-            pp.allreduce_grads(net.layers.parameters())
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
 
     for _ in range(args.warmup):
         proc_step()
-    sync_all()
-    # per-kernel CUDA-event split of the step (roofline.kernels): eager, outside the timed region when the timed
-    # region replays a CUDA graph (events cannot be captured), inside it otherwise
-    use_graph = args.graph == "on" or (args.graph == "auto" and world > 1)
-    timed_step, prof, prof_steps, graphed = proc_step, None, args.steps, False
-    if use_graph:
-        ops.PROFILE.reset(enabled=True)
-        proc_step()
-        prof, prof_steps = ops.PROFILE.summary(), 1
-        ops.PROFILE.reset(enabled=False)
-        sync_all()
-        try:
-            from aero_gnn_b200.graphs import GraphedStep
-            timed_step = GraphedStep(proc_step, warmup=1)
-            graphed = True
-            for _ in range(2):
-                timed_step()
-        except Exception as exc:   # noqa: BLE001 -- report and time the eager step instead
-            print(f"[bench] CUDA-graph capture failed on rank {rank}: {exc!r}; timing the eager step", file=sys.stderr)
-            timed_step = proc_step
-        if world > 1:   # every rank must time the same kind of step (a graph replay and an eager step both post the
-            flag = torch.tensor([1 if graphed else 0], device=dev)   # same NCCL operations, so mixing would still run)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if int(flag.item()) == 0:
-                timed_step, graphed = proc_step, False
-        sync_all()
-    else:
-        ops.PROFILE.reset(enabled=True)
+    timer.sync()
+    # per-kernel CUDA-event split of the step (roofline.kernels): one eager step OUTSIDE the timed region (events cannot
+    # be captured into a graph, and recording them inside the timed loop would perturb it)
+    ops.PROFILE.reset(enabled=True)
+    proc_step()
+    prof = ops.PROFILE.summary()
+    ops.PROFILE.reset(enabled=False)
+    timer.sync()
+    ms_prof_step = timer.run(proc_step, 1)              # the eager step the event split refers to
+    timed, is_graph = graphed(proc_step, world, dev, rank, args.graph != "off")
+    holder["g"] = timed
     l0 = ops.LaunchCounter.total
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        timed_step()
-    ev1.record()
-    sync_all()
-    ms = ev0.elapsed_time(ev1) / args.steps
+    ms = timer.run(timed, args.steps)
     launches = ops.LaunchCounter.total - l0
     clocks = sampler.stop() if rank == 0 else None
-    if prof is None:
-        prof = ops.PROFILE.summary()
-    ops.PROFILE.reset(enabled=False)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     value = E / (ms * 1e-3)
 
     # ---- end-to-end through the public API: pinned host -> device, model fwd, loss, bwd, loss readback ----
     e2e = None
-    if not args.no_e2e and world == 1:
-        host = [mesh.node_attr.pin_memory(), mesh.edge_attr.pin_memory(), mesh.edge_index.pin_memory(),
-                mesh.target.pin_memory()]
+    if not args.no_e2e:
+        if world == 1:
+            host = [mesh.node_attr.pin_memory(), mesh.edge_attr.pin_memory(), mesh.edge_index.pin_memory(),
+                    mesh.target.pin_memory()]
+
+            def e2e_step(bufs):
+                na, ea, ei, tg = bufs
+                net.zero_grad(set_to_none=True)
+                pred = net(na.to(dt), ea.to(dt), ei)
+                loss = mse_loss(pred, tg)
+                loss.backward()
+                return loss
+            api = "MeshGraphNet.forward + MSE loss + backward (encoders/decoder included)"
+        else:
+            # this rank's shard of the raw inputs: own node rows, its edges' features (caller order), own targets;
+            # the partition (halo plan + local CSR) is built once per mesh, like the graph plan at N = 1
+            eids = torch.from_numpy(pp.halo.edge_ids)
+            host = [mesh.node_attr[pp.lo:pp.hi].contiguous().pin_memory(), mesh.edge_attr[eids].contiguous().pin_memory(),
+                    mesh.target[pp.lo:pp.hi].contiguous().pin_memory()]
+            other = [p for n_, p in net.named_parameters() if not n_.startswith("layers.")]
+            frac = pp.n_own / N
+
+            def e2e_step(bufs):
+                na, ea, tg = bufs
+                net.zero_grad(set_to_none=True)
+                x = net.node_encoder(na.to(dt))
+                e = net.edge_encoder(permute_rows(ea.to(dt), pp.plan.perm, pp.plan.inv_perm))
+                x, _ = pp.run(net.layers, x, e)
+                pred = net.decoder(x)
+                loss = mse_loss(pred, tg, scale=frac)        # the ranks' losses add up to the global mean
+                loss.backward()
+                pp.allreduce_grads(other)
+                dist.all_reduce(loss)
+                return loss
+            api = ("encoders + partitioned processor (halo exchange) + decoder + MSE loss + backward + gradient "
+                   "all-reduce, every rank on its shard of the raw inputs")
         h2d = sum(t.numel() * t.element_size() for t in host)
-        lossf = torch.nn.MSELoss()
-
-        # Input pipeline as a training loop with a pinned-memory loader runs it: the copy of step i+1's inputs is
-        # issued on a copy stream while step i computes (every step still copies its own 236 MB inside the timed
-        # region and reads its loss back); two device buffers alternate.
-        copy_stream = torch.cuda.Stream()
-        bufs = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        freed = [torch.cuda.Event(), torch.cuda.Event()]
-
-        def issue_copy(slot):
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(freed[slot])          # the step that last read this buffer has finished
-                for d, h in zip(bufs[slot], host):
-                    d.copy_(h, non_blocking=True)
-                ready[slot].record(copy_stream)
-
-        def e2e_step(i):
-            slot = i & 1
-            torch.cuda.current_stream().wait_event(ready[slot])
-            issue_copy(slot ^ 1)                             # next step's inputs travel under this step's compute
-            na, ea, ei, tg = bufs[slot]
-            net.zero_grad(set_to_none=True)
-            pred = net(na.to(dt), ea.to(dt), ei)
-            loss = lossf(pred.float(), tg)
-            loss.backward()
-            freed[slot].record()
-            return float(loss.item())
-
-        for ev in freed:
-            ev.record()
-        issue_copy(0)
-        n_warm = max(1, min(args.warmup, 2))
-        for i in range(n_warm):
-            e2e_step(i)
-        torch.cuda.synchronize()
-        n_e2e = max(1, min(args.steps, 3))
-        t0 = time.perf_counter()
-        for i in range(n_warm, n_warm + n_e2e):
-            e2e_step(i)
-        torch.cuda.synchronize()
-        e2e_s = (time.perf_counter() - t0) / n_e2e
-        e2e = {"value": E / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-               "ms_per_step": e2e_s * 1e3, "api": "MeshGraphNet.forward + MSELoss + backward (encoders/decoder included)",
+        n_warm, n_e2e = max(1, min(args.warmup, 2)), max(3, min(args.steps, 10))
+        e2e_s = e2e_pipeline(host, dev, e2e_step, n_e2e, n_warm)
+        if world > 1:
+            t = torch.tensor([e2e_s, float(h2d)], device=dev, dtype=torch.float64)
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t)
+            e2e_s, h2d = float(tmax[0].item()), int(t[1].item())
+        e2e = {"value": E / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * world,
+               "ms_per_step": e2e_s * 1e3, "steps": n_e2e, "api": api,
                "input_pipeline": "pinned host -> device on a copy stream, one step ahead (double buffered)"}
 
-    def shutdown():
-        """Tear the process group down.  Captured graphs that contain NCCL kernels must be released first, and a
-        watchdog bounds the teardown: the result line is already printed, a wedged communicator must not hang the job."""
-        nonlocal timed_step
-        if world <= 1:
-            return
-        dog = threading.Timer(45.0, lambda: os._exit(0))
-        dog.daemon = True
-        dog.start()
-        timed_step = None
-        import gc
-        gc.collect()
-        torch.cuda.synchronize()
-        dist.barrier()
-        dist.destroy_process_group()
-        dog.cancel()
-
     if rank != 0:
-        shutdown()
+        shutdown(world, holder)
         return
 
     hbm, tc, which = peaks()
-    # dominant kernel = the fused block launch with the largest share of the step
-    dom = max(prof, key=lambda k: prof[k]["ms_total"]) if prof else None
-    roof = None
-    if dom:
-        n_rows_E = E if world == 1 else pp.E_loc
-        n_rows_N = N if world == 1 else pp.n_own
-        ab = kernel_alg_bytes(dom, n_rows_E, n_rows_N, b)
-        avg_ms = prof[dom]["ms_total"] / max(prof[dom]["count"], 1)
-        ach = ab / (avg_ms * 1e-3) / 1e9
-        traffic = None   # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same workload)
-        tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-        if world == 1 and os.path.exists(tp):
-            tj = json.load(open(tp))
-            if tj["workload"] == {"N": N, "E": E, "dtype": args.dtype} and dom in tj:
-                traffic = tj[dom]["read_bytes"] + tj[dom]["write_bytes"]
-        # SURVEY.md 8(d): roofline = max(bytes term, flops term).  The fused bf16 kernels sit past the ridge
-        # (algorithmic 338 flop/B for the edge backward vs a measured ridge of 221 flop/B), fp32 rows below it, so
-        # both terms are always reported and the top-level tuple is the binding (larger) one.
-        af = kernel_alg_flops(dom, n_rows_E, n_rows_N, CFG["num_hidden_layers_edge_processor"])
-        tfl = af / (avg_ms * 1e-3) / 1e12
-        term_hbm = {"achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm}
-        term_tc = {"achieved": tfl, "peak": tc, "unit": "TFLOP/s", "frac": tfl / tc,
-                   "peak_kind": "sustained dense bf16 (kernel timed inside a long step)"}
-        tensor_bound = dt == torch.bfloat16 and term_tc["frac"] > term_hbm["frac"]
-        top = term_tc if tensor_bound else term_hbm
-        roof = {"bound": "tensor" if tensor_bound else "hbm", "kernel": dom, "achieved": top["achieved"],
-                "peak": top["peak"], "unit": top["unit"], "frac": top["frac"],
-                "hbm_term": term_hbm, "tensor_term": term_tc, "algorithmic_flops": af,
-                "peak_source": which, "traffic": traffic, "algorithmic_bytes": ab, "avg_ms_per_launch": avg_ms,
-                "share_of_step": prof[dom]["ms_total"] / (ms * prof_steps),
-                "kernels": {k: {"avg_ms": v["ms_total"] / max(v["count"], 1), "share": v["ms_total"] / (ms * prof_steps)}
-                            for k, v in prof.items()},
-                "step_alg_gbytes": alg_bytes_step(E, N, b) / 1e9,
-                "step_frac_hbm": alg_bytes_step(E, N, b) / world / (ms * 1e-3) / 1e9 / hbm,
-                # SURVEY.md 8(d): F_fwd = 131,072 E + 229,376 N per step (L = 2), fwd+bwd = 3x, 15 steps
-                "step_alg_tflop": 45 * (131072 * E + 229376 * N) / 1e12,
-                "step_frac_tensor": 45 * (131072 * E + 229376 * N) / world / (ms * 1e-3) / 1e12 / tc}
+    dom = max((k for k in prof if k in ("edge_fwd", "edge_bwd", "node_fwd", "node_bwd")), key=lambda k: prof[k]["ms_total"])
+    n_rows_E = E if world == 1 else pp.E_loc
+    n_rows_N = N if world == 1 else pp.n_own
+    ab = kernel_alg_bytes(dom, n_rows_E, n_rows_N, b)
+    avg_ms = prof[dom]["ms_total"] / max(prof[dom]["count"], 1)
+    ach = ab / (avg_ms * 1e-3) / 1e9
+    traffic, traffic_note = ncu_traffic(dom, N, E, args.dtype) if world == 1 else (None, None)
+    # roofline = max(bytes term, flops term).  The fused bf16 kernels sit past the ridge (algorithmic
+    # 338 flop/B for the edge backward vs a measured ridge of 221 flop/B), fp32 rows below it, so both terms are always
+    # reported and the top-level tuple is the binding (larger) one.
+    af = kernel_alg_flops(dom, n_rows_E, n_rows_N, CFG["num_hidden_layers_edge_processor"])
+    tfl = af / (avg_ms * 1e-3) / 1e12
+    term_hbm = {"achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm}
+    term_tc = {"achieved": tfl, "peak": tc, "unit": "TFLOP/s", "frac": tfl / tc,
+               "peak_kind": "sustained dense bf16 (kernel timed inside a long step)"}
+    tensor_bound = dt == torch.bfloat16 and term_tc["frac"] > term_hbm["frac"]
+    top = term_tc if tensor_bound else term_hbm
+    roof = {"bound": "tensor" if tensor_bound else "hbm", "kernel": dom, "achieved": top["achieved"],
+            "peak": top["peak"], "unit": top["unit"], "frac": top["frac"],
+            "hbm_term": term_hbm, "tensor_term": term_tc, "algorithmic_flops": af,
+            "peak_source": which, "traffic": traffic, "traffic_capture": traffic_note, "algorithmic_bytes": ab,
+            "avg_ms_per_launch": avg_ms,
+            "timing": "CUDA events around every fused block launch of one eager step (same stream), outside the timed region",
+            "share_of_step": prof[dom]["ms_total"] / ms_prof_step, "eager_step_ms": ms_prof_step,
+            "kernels": {k: {"avg_ms": v["ms_total"] / max(v["count"], 1), "share": v["ms_total"] / ms_prof_step}
+                        for k, v in prof.items()},
+            "step_alg_gbytes": alg_bytes_step(E, N, b) / 1e9,
+            "step_frac_hbm": alg_bytes_step(E, N, b) / world / (ms * 1e-3) / 1e9 / hbm,
+            # F_fwd = 131,072 E + 229,376 N per step (L = 2), fwd+bwd = 3x, 15 steps
+            "step_alg_tflop": 45 * (131072 * E + 229376 * N) / 1e12,
+            "step_frac_tensor": 45 * (131072 * E + 229376 * N) / world / (ms * 1e-3) / 1e12 / tc}
     cpu = None
     if not args.no_cpu and world == 1:
         threads = os.cpu_count() or 1
         r = cpu_arm(3, 1, 20.0, threads)       # bounded: ~20 s of host work (1 warm-up + 3 timed layer steps)
         cpu = {"value": r["value"], "unit": "edges/s", "cores": threads, "kind": r["kind"], "sample": r["sample"]}
 
-    line = {"metric": "MGN-15 processor edges/sec (fwd+bwd)", "value": value, "unit": "edges/s", "n_gpus": world,
+    line = {"metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "edge_steps_per_s": 15 * value,
-            "config": {"workload": workload_desc(N, E),
-                       "parallelism": parallelism_desc(world), "l2": "inputs (>1.7 GB of latents per step) are larger than L2",
-                       "path": "umma" if lib.load().aero_has_umma() and dt == torch.bfloat16 else "simt",
-                       "launch": "one CUDA graph replay per step" if graphed else "eager launches"},
+            "config": {"workload": workload_desc("c5", N, E), "parallelism": parallelism_desc("c5", world)},
+            "run": {"l2": "inputs (>1.7 GB of latents per step) are larger than L2",
+                    "path": "umma" if lib.load().aero_has_umma() and dt == torch.bfloat16 else "simt",
+                    "launch": "one CUDA graph replay per step" if is_graph else "eager launches"},
             "clocks": clocks, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e}
     print(json.dumps(line), flush=True)
-    shutdown()
+    shutdown(world, holder)
+
+
+# ---------------------------------------------------------------------------------------------------
+def bench_c2(args, rank, world, local, dev):
+    """Whole training step on a batch of 8 airfoil meshes per rank, data-parallel (train.py:50-51, utils.py:171-196)."""
+    import torch.distributed as dist
+    from aero_gnn_b200 import lib, ops, processor
+    import aero_gnn_b200.models as M
+    from aero_gnn_b200.meshes import airfoil_o_mesh, batch_meshes
+    from aero_gnn_b200.train_tail import FusedAdam, mse_loss
+
+    dt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    mesh = batch_meshes([airfoil_o_mesh(100, 50, seed=8 * rank + s) for s in range(8)])     # 8 meshes per rank (weak)
+    N, E = mesh.num_nodes, mesh.num_edges
+    torch.manual_seed(0)
+    net = M.MeshGraphNet(6, 3, 4, **CFG).to(dev).to(dt)
+    opt = FusedAdam(net.parameters(), lr=1e-3)
+    other = [p for n_, p in net.named_parameters() if not n_.startswith("layers.")]
+    timer = Timer(dev, world, rank)
+    if world > 1:
+        # processor-stack gradients: flat fp32 buckets of 5 steps, all-reduced while the earlier steps' backward runs;
+        # the mean over ranks is folded into the loss scale
+        processor.set_grad_reduce(lambda t: dist.all_reduce(t, async_op=True), 5)
+
+    def reduce_other():
+        flat = torch.cat([p.grad.reshape(-1).float() for p in other])
+        dist.all_reduce(flat)
+        off, views = 0, []
+        for p in other:
+            views.append(flat[off: off + p.numel()].view_as(p.grad))
+            off += p.numel()
+        torch._foreach_copy_([p.grad for p in other], views)
+
+    na, ea, ei, tg = (mesh.node_attr.to(dev, dt), mesh.edge_attr.to(dev, dt), mesh.edge_index.to(dev), mesh.target.to(dev))
+    ops.PLAN_CACHE.get(ei, N)
+    loss_acc = torch.zeros((), device=dev)
+
+    def train_step(bufs=None):
+        a, b_, i_, t_ = (na, ea, ei, tg) if bufs is None else (bufs[0].to(dt), bufs[1].to(dt), bufs[2], bufs[3])
+        opt.zero_grad(set_to_none=True)
+        loss = mse_loss(net(a, b_, i_), t_, scale=1.0 / world)
+        loss.backward()
+        if world > 1:
+            reduce_other()
+        opt.step()
+        loss_acc.add_(loss.detach())       # accumulated on the device: no per-batch host sync (utils.py:195 has one)
+        return loss
+
+    for _ in range(args.warmup):
+        train_step()
+    timer.sync()
+    l0 = ops.LaunchCounter.total
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timer.run(train_step, args.steps)
+    launches = ops.LaunchCounter.total - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * E / (ms * 1e-3)
+    host = [mesh.node_attr.pin_memory(), mesh.edge_attr.pin_memory(), mesh.edge_index.pin_memory(), mesh.target.pin_memory()]
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    e2e_s = e2e_pipeline(host, dev, train_step, max(3, min(args.steps, 20)), 2)
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    if rank == 0:
+        line = {"metric": "MGN-15 training edges/sec (fwd+bwd+optimizer)", "value": value, "unit": "edges/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+                "data": "synthetic",
+                "config": {"workload": workload_desc("c2", N, E), "parallelism": parallelism_desc("c2", world)},
+                "run": {"launch": "eager launches", "l2": "70 MB of latents per step: partly L2-resident (stated, not flushed)",
+                        "path": "umma" if lib.load().aero_has_umma() and dt == torch.bfloat16 else "simt",
+                        "optimizer": "aero_adam_step (one launch), loss aero_mse_loss_grad, no per-step host sync"},
+                "clocks": clocks, "gpu_launches": launches, "roofline": None, "cpu_baseline": None,
+                "e2e": {"value": world * E / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": h2d * world,
+                        "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_s * 1e3,
+                        "api": "MeshGraphNet.forward + mse_loss + backward + FusedAdam.step, inputs from pinned host memory, loss read back"}}
+        print(json.dumps(line), flush=True)
+    shutdown(world, {})
+
+
+def bench_c3(args, rank, world, local, dev):
+    """BSMS-MGN (models/bsms_mgn.py) forward + backward on the 100k-node airfoil mesh; replicas only at N > 1."""
+    import torch.distributed as dist
+    from aero_gnn_b200 import lib, ops
+    import aero_gnn_b200.models as M
+    from aero_gnn_b200.meshes import airfoil_o_mesh
+    from aero_gnn_b200.train_tail import mse_loss
+
+    dt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    mesh = airfoil_o_mesh(400, 250, seed=0)
+    N, E = mesh.num_nodes, mesh.num_edges
+    torch.manual_seed(0)
+    net = M.BiStridedMeshGraphNet(6, 3, 4, num_scales=4, layers_per_scale=2, stride=2, **dict(CFG)).to(dev).to(dt)
+    na, ea, ei, tg = mesh.node_attr.to(dev, dt), mesh.edge_attr.to(dev, dt), mesh.edge_index.to(dev), mesh.target.to(dev)
+    batch, pos = mesh.batch.to(dev), mesh.pos.to(dev)
+    timer = Timer(dev, world, rank)
+
+    def step(bufs=None):
+        a, b_ = (na, ea) if bufs is None else (bufs[0].to(dt), bufs[1].to(dt))
+        net.zero_grad(set_to_none=True)
+        loss = mse_loss(net(a, b_, ei, batch, pos), tg)
+        loss.backward()
+        return loss
+
+    for _ in range(args.warmup):
+        step()
+    timer.sync()
+    l0 = ops.LaunchCounter.total
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timer.run(step, args.steps)
+    launches = ops.LaunchCounter.total - l0
+    clocks = sampler.stop() if rank == 0 else None
+    host = [mesh.node_attr.pin_memory(), mesh.edge_attr.pin_memory()]
+    e2e_s = e2e_pipeline(host, dev, step, max(3, min(args.steps, 10)), 2)
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    if rank == 0:
+        h2d = sum(t.numel() * t.element_size() for t in host)
+        line = {"metric": "BSMS-MGN edges/sec (fwd+bwd)", "value": world * E / (ms * 1e-3), "unit": "edges/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": workload_desc("c3", N, E), "parallelism": parallelism_desc("c3", world)},
+                "run": {"launch": "eager launches", "hierarchy": "pool levels cached per mesh (content hash)",
+                        "path": "umma" if lib.load().aero_has_umma() and dt == torch.bfloat16 else "simt"},
+                "clocks": clocks, "gpu_launches": launches, "roofline": None, "cpu_baseline": None,
+                "e2e": {"value": world * E / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": h2d * world,
+                        "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_s * 1e3,
+                        "api": "BiStridedMeshGraphNet.forward + mse_loss + backward, features from pinned host memory"}}
+        print(json.dumps(line), flush=True)
+    shutdown(world, {})
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c5", choices=["c5", "c2", "c3"])
+    ap.add_argument("--nu", type=int, default=1000)
+    ap.add_argument("--nv", type=int, default=1000)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--graph", default="on", choices=["auto", "on", "off"],
+                    help="replay the C5 processor step as one CUDA graph (default at every N, so the 1 -> 8 scaling "
+                         "curve compares like with like); off = eager launches")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from aero_gnn_b200 import lib
+    lib.load()          # fails loudly when libaero_sm100.so is missing: there is no fallback path
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    {"c5": bench_c5, "c2": bench_c2, "c3": bench_c3}[args.config](args, rank, world, local, dev)
 
 
 if __name__ == "__main__":

@@ -315,6 +315,33 @@ size_t aero_wec_workspace_bytes(const aero_wec_desc* d, int backward);
 int aero_wec_fwd(const aero_wec_desc* d, void* stream);
 int aero_wec_bwd(const aero_wec_desc* d, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training-step tail (utils.py:191-195, train.py:207-211, :222).
+ *
+ * aero_mse_loss_grad: loss[0] = loss_scale * sum (pred - target)^2 and grad = grad_scale * (pred - target) in one pass
+ *   (nn.MSELoss mean reduction + its backward: loss_scale = 1/(rows*cols), grad_scale = 2/(rows*cols)); `pred` /
+ *   `grad` rows may be strided (ld_* elements, e.g. the first `cols` columns of a 128-wide decoder tile); target is
+ *   fp32 contiguous [rows, cols]; the loss stays on the device (no per-batch host sync); fixed-order reduction.
+ * aero_adam_step: ONE launch updates every parameter tensor listed in the device-resident table `segs_device`
+ *   (torch.optim.Adam semantics: g += weight_decay * w; m, v moments; w -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)).
+ *   A segment with grad == NULL is skipped; master != NULL keeps an fp32 master copy of a bf16 parameter.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct aero_adam_seg {
+  void* param;        /* [n] p_dtype, updated in place            */
+  const void* grad;   /* [n] g_dtype, or NULL (no gradient)       */
+  float* m;           /* [n] fp32 first moment                    */
+  float* v;           /* [n] fp32 second moment                   */
+  float* master;      /* [n] fp32 master weights, or NULL         */
+  int64_t n;
+  int32_t p_dtype, g_dtype;
+} aero_adam_seg;
+size_t aero_mse_workspace_bytes(void);
+int aero_mse_loss_grad(const void* pred, const float* target, void* grad, float* loss, int64_t rows, int64_t cols,
+                       int64_t ld_pred, int64_t ld_grad, int dtype, float loss_scale, float grad_scale,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int aero_adam_step(const aero_adam_seg* segs_device, int n_segs, int64_t max_elems, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
