@@ -69,10 +69,20 @@ __device__ __forceinline__ void adam_elems(const aero_adam_seg& s, float lr_c, f
   }
 }
 
-__global__ void __launch_bounds__(256) adam_kernel(const aero_adam_seg* __restrict__ segs, float lr_c, float b1, float b2,
-                                                   float eps, float wd, float inv_sqrt_c2) {
+// Per-tensor step counts (torch.optim.Adam keeps one per parameter: a parameter without a gradient skips the step
+// and its bias corrections lag).  steps_in is read by every block of a segment, steps_out written by one thread, the
+// caller swaps the two arrays between launches -- no race, no second launch.
+__global__ void __launch_bounds__(256) adam_kernel(const aero_adam_seg* __restrict__ segs, const int32_t* __restrict__ steps_in,
+                                                   int32_t* __restrict__ steps_out, float lr, float b1, float b2, float eps,
+                                                   float wd) {
   const aero_adam_seg s = segs[blockIdx.y];
-  if (s.grad == nullptr || s.n == 0) return;
+  const int t_prev = steps_in[blockIdx.y];
+  const bool live = s.grad != nullptr && s.n > 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) steps_out[blockIdx.y] = t_prev + (live ? 1 : 0);
+  if (!live) return;
+  // bias corrections in double, as torch computes them in Python floats
+  const double c1 = 1.0 - pow((double)b1, (double)(t_prev + 1)), c2 = 1.0 - pow((double)b2, (double)(t_prev + 1));
+  const float lr_c = (float)((double)lr / c1), inv_sqrt_c2 = (float)(1.0 / sqrt(c2));
   if (s.p_dtype == AERO_F32) {
     if (s.g_dtype == AERO_F32) adam_elems<float, float>(s, lr_c, b1, b2, eps, wd, inv_sqrt_c2);
     else adam_elems<float, __nv_bfloat16>(s, lr_c, b1, b2, eps, wd, inv_sqrt_c2);
@@ -115,19 +125,18 @@ extern "C" int aero_mse_loss_grad(const void* pred, const float* target, void* g
   return AERO_OK;
 }
 
-extern "C" int aero_adam_step(const aero_adam_seg* segs_device, int n_segs, int64_t max_elems, float lr, float beta1,
-                              float beta2, float eps, float weight_decay, int64_t step, void* stream) {
+extern "C" int aero_adam_step(const aero_adam_seg* segs_device, int n_segs, int64_t max_elems, const int32_t* steps_in,
+                              int32_t* steps_out, float lr, float beta1, float beta2, float eps, float weight_decay,
+                              void* stream) {
   g_launch_count = 0;
-  AERO_CHECK_ARG(n_segs >= 0 && n_segs <= 65535 && (n_segs == 0 || segs_device) && step >= 1 && max_elems >= 0,
+  AERO_CHECK_ARG(n_segs >= 0 && n_segs <= 65535 && (n_segs == 0 || (segs_device && steps_in && steps_out)) &&
+                     steps_in != steps_out && max_elems >= 0,
                  "aero_adam_step: bad arguments");
   if (n_segs == 0) return AERO_OK;
-  // bias corrections in double on the host (torch computes them in Python floats)
-  const double c1 = 1.0 - pow((double)beta1, (double)step), c2 = 1.0 - pow((double)beta2, (double)step);
   int64_t bx = cdiv(max_elems > 0 ? max_elems : 1, 256 * 4);
   if (bx > 32) bx = 32;
   dim3 grid((unsigned)bx, (unsigned)n_segs);
-  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(segs_device, (float)(lr / c1), beta1, beta2, eps, weight_decay,
-                                                     (float)(1.0 / sqrt(c2)));
+  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(segs_device, steps_in, steps_out, lr, beta1, beta2, eps, weight_decay);
   AERO_LAUNCH_CHECK();
   return AERO_OK;
 }

@@ -109,8 +109,8 @@ SIGNATURES = {
     "aero_mse_workspace_bytes": (C.c_size_t, []),
     "aero_mse_loss_grad": (C.c_int, [C.c_void_p] * 4 + [C.c_int64] * 4 + [C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_size_t,
                                       C.c_void_p]),
-    "aero_adam_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
-                                 C.c_int64, C.c_void_p]),
+    "aero_adam_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                 C.c_float, C.c_float, C.c_void_p]),
     "aero_wec_workspace_bytes": (C.c_size_t, [C.POINTER(WecDesc), C.c_int]),
     "aero_wec_fwd": (C.c_int, [C.POINTER(WecDesc), C.c_void_p]),
     "aero_wec_bwd": (C.c_int, [C.POINTER(WecDesc), C.c_void_p]),

@@ -76,8 +76,13 @@ class FusedAdam:
         if master_weights and any(p.dtype != torch.float32 for p in self.params):
             self.master = torch.cat([p.detach().reshape(-1).float() for p in self.params])
         self._table_dev = torch.empty(len(self.params) * C.sizeof(_l.AdamSeg), dtype=torch.uint8, device=dev)
-        self._table_host = torch.empty(len(self.params) * C.sizeof(_l.AdamSeg), dtype=torch.uint8).pin_memory()
-        self._key, self._copied = None, None
+        # pinned staging for the table upload; four buffers rotate so a rebuild never rewrites bytes an earlier
+        # asynchronous upload may still be reading (no host-side event wait, which a CUDA-graph capture forbids)
+        self._table_hosts = [torch.empty(len(self.params) * C.sizeof(_l.AdamSeg), dtype=torch.uint8).pin_memory()
+                             for _ in range(4)]
+        self._table_turn = 0
+        self._key = None
+        self._steps = [torch.zeros(len(self.params), dtype=torch.int32, device=dev) for _ in range(2)]
         self.max_elems = max(p.numel() for p in self.params)
         self.param_groups = [{"lr": self.lr, "params": self.params}]     # what lr schedulers touch
 
@@ -87,9 +92,9 @@ class FusedAdam:
                      0 if p.grad is None else ops.dtype_code(p.grad)) for p in self.params)
         if key == self._key:
             return
-        if self._copied is not None:
-            self._copied.synchronize()        # the previous upload has left the pinned staging buffer
-        segs = (_l.AdamSeg * len(self.params)).from_buffer(self._table_host.numpy())
+        host = self._table_hosts[self._table_turn % 4]
+        self._table_turn += 1
+        segs = (_l.AdamSeg * len(self.params)).from_buffer(host.numpy())
         off = 0
         for i, p in enumerate(self.params):
             n = p.numel()
@@ -102,9 +107,7 @@ class FusedAdam:
             s.n, s.p_dtype = n, ops.dtype_code(p)
             s.g_dtype = ops.dtype_code(p.grad) if p.grad is not None else s.p_dtype
             off += n
-        self._table_dev.copy_(self._table_host, non_blocking=True)
-        self._copied = torch.cuda.Event()
-        self._copied.record()
+        self._table_dev.copy_(host, non_blocking=True)
         self._key = key
 
     @torch.no_grad()
@@ -114,8 +117,10 @@ class FusedAdam:
         self.step_count += 1
         lib = _l.load()
         with torch.cuda.device(self._table_dev.device):
-            rc = lib.aero_adam_step(ops._ptr(self._table_dev), len(self.params), self.max_elems, self.lr, self.betas[0],
-                                    self.betas[1], self.eps, self.weight_decay, self.step_count, ops._stream())
+            rc = lib.aero_adam_step(ops._ptr(self._table_dev), len(self.params), self.max_elems,
+                                    ops._ptr(self._steps[0]), ops._ptr(self._steps[1]), self.lr, self.betas[0],
+                                    self.betas[1], self.eps, self.weight_decay, ops._stream())
+        self._steps.reverse()
         _l.check(rc, "aero_adam_step")
         ops.LaunchCounter.add()
 
@@ -128,11 +133,12 @@ class FusedAdam:
                     p.grad.zero_()
 
     def state_dict(self):
-        return {"step": self.step_count, "m": self.m, "v": self.v, "master": self.master, "lr": self.lr,
+        return {"step": self.step_count, "steps": self._steps[0], "m": self.m, "v": self.v, "master": self.master, "lr": self.lr,
                 "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay}
 
     def load_state_dict(self, sd) -> None:
         self.step_count = int(sd["step"])
+        self._steps[0].copy_(sd["steps"])
         self.m.copy_(sd["m"])
         self.v.copy_(sd["v"])
         if self.master is not None and sd.get("master") is not None:

@@ -325,6 +325,8 @@ int aero_wec_bwd(const aero_wec_desc* d, void* stream);
  * aero_adam_step: ONE launch updates every parameter tensor listed in the device-resident table `segs_device`
  *   (torch.optim.Adam semantics: g += weight_decay * w; m, v moments; w -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)).
  *   A segment with grad == NULL is skipped; master != NULL keeps an fp32 master copy of a bf16 parameter.
+ *   steps_in / steps_out: device int32 [n_segs], the number of updates each tensor has had (torch keeps one step count
+ *   per parameter); the launch reads steps_in and writes steps_out (two distinct arrays the caller swaps).
  * ------------------------------------------------------------------------------------------ */
 typedef struct aero_adam_seg {
   void* param;        /* [n] p_dtype, updated in place            */
@@ -339,8 +341,8 @@ size_t aero_mse_workspace_bytes(void);
 int aero_mse_loss_grad(const void* pred, const float* target, void* grad, float* loss, int64_t rows, int64_t cols,
                        int64_t ld_pred, int64_t ld_grad, int dtype, float loss_scale, float grad_scale,
                        void* workspace, size_t workspace_bytes, void* stream);
-int aero_adam_step(const aero_adam_seg* segs_device, int n_segs, int64_t max_elems, float lr, float beta1, float beta2,
-                   float eps, float weight_decay, int64_t step, void* stream);
+int aero_adam_step(const aero_adam_seg* segs_device, int n_segs, int64_t max_elems, const int32_t* steps_in,
+                   int32_t* steps_out, float lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
 
 #ifdef __cplusplus
 }
