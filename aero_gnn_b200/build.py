@@ -16,9 +16,11 @@ CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
 BUILD = PKG / "build"
 LIB = PKG / "libaero_sm100.so"
+PROBE_LIB = PKG / "libaero_probe.so"     # hardware probes (include/aero_gnn_debug.h): diagnostics, not in the product library
+PROBE_SOURCES = ["umma_probe.cu"]
 
 SOURCES = ["abi.cu", "sort_plan.cu", "segment.cu", "block_simt.cu", "block_umma.cu", "block_umma_bwd.cu", "block_umma_bwd2.cu",
-           "umma_probe.cu", "bistride.cu", "train_tail.cu"]
+           "bistride.cu", "train_tail.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -43,7 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     BUILD.mkdir(exist_ok=True)
     headers = list(CSRC.glob("*.cuh")) + list(INCLUDE.glob("*.h"))
     jobs = []
-    for s in SOURCES:
+    for s in SOURCES + PROBE_SOURCES:
         src = CSRC / s
         obj = BUILD / (s + ".o")
         stale = force or _newer(src, obj) or any(_newer(h, obj) for h in headers)
@@ -71,6 +73,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    if jobs or not PROBE_LIB.exists():
+        # the probes use the product library's error plumbing: link against it, found next to the probe library
+        cmd = [_nvcc(), "-shared", "-o", str(PROBE_LIB), *[str(BUILD / (s + ".o")) for s in PROBE_SOURCES],
+               "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared", f"-L{PKG}", "-l:libaero_sm100.so",
+               "-Xlinker", "-rpath=$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"probe link failed:\n{r.stdout}\n{r.stderr}")
     return LIB
 
 

@@ -73,8 +73,6 @@ SIGNATURES = {
     "aero_has_umma": (C.c_int, []),
     "aero_has_umma_bwd": (C.c_int, []),
     "aero_umma_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
-    "aero_umma_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
-    "aero_umma_rate_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "aero_last_launch_count": (C.c_int, []),
     "aero_graph_plan_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "aero_graph_plan_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 7 + [C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -116,7 +114,30 @@ SIGNATURES = {
     "aero_wec_bwd": (C.c_int, [C.POINTER(WecDesc), C.c_void_p]),
 }
 
+# hardware probes: a separate debug library (include/aero_gnn_debug.h), never needed by the product path
+PROBE_LIB_PATH = PKG / "libaero_probe.so"
+PROBE_SIGNATURES = {
+    "aero_umma_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "aero_umma_rate_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+}
+
 _lib = None
+_probe = None
+
+
+def load_probe() -> C.CDLL:
+    """dlopen libaero_probe.so (after the product library it links against)."""
+    global _probe
+    if _probe is None:
+        load()
+        if not PROBE_LIB_PATH.exists():
+            raise RuntimeError(f"{PROBE_LIB_PATH} is missing: build it with `python -m aero_gnn_b200.build`")
+        lib = C.CDLL(str(PROBE_LIB_PATH))
+        for name, (res, args) in PROBE_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _probe = lib
+    return _probe
 
 
 def load() -> C.CDLL:

@@ -106,13 +106,13 @@ class GMP(nn.Module):
                                       nn.Linear(hidden_dim, node_dim), nn.LayerNorm(node_dim))
 
     def stack_config(self) -> StackConfig:
-        if self.activation != "relu":
-            raise RuntimeError("GMP(activation='silu'): SiLU's derivative is not a function of its output, which the fused "
-                               "sm_100a block kernels rely on; only 'relu' is supported (no fallback)")
         if not (self.dims[0] == self.dims[1] == self.dims[2] == D):
             raise RuntimeError(f"the fused sm_100a path supports node_dim == edge_dim == hidden_dim == {D} only "
                                f"(got {self.dims})")
-        return StackConfig(L_edge=0, L_node=0, act_edge="relu", act_node="relu", use_ln=True, mean=False)
+        # 'relu' runs on the fused block kernels; 'silu' (the bytecode's other choice, bistride_ops orig :216: ReLU if
+        # activation == 'relu' else SiLU) has no derivative-from-output form and runs processor.eager_stack (announced)
+        act = "relu" if self.activation == "relu" else "silu"
+        return StackConfig(L_edge=0, L_node=0, act_edge=act, act_node=act, use_ln=True, mean=False)
 
     def step_weights(self, dtype: torch.dtype) -> StepWeights:
         def build():

@@ -63,6 +63,13 @@ class MLP(nn.Module):
             z = self.layers[0](x)                      # [rows, in] x [in, 128]: a thin library GEMM, bias included
             return dense_tail(len(hidden), self.activation_name, self.use_layer_norm, z, hidden, w_out, b_out,
                               gamma, beta)
+        # shapes / activations the fused kernel does not cover: a dense row-wise chain of library ops on the GPU,
+        # announced once and counted (never silent; ops.Fallbacks)
+        from ..ops import Fallbacks
+        Fallbacks.note("mlp_library_chain",
+                       f"MLP {[l.in_features for l in self.layers]} -> {self.layers[-1].out_features} "
+                       f"(activation '{self.activation_name}') is outside the fused block kernel (128-wide layers, "
+                       f"relu/tanh/sigmoid/elu/leaky_relu)")
         last = len(self.layers) - 1
         for i, lin in enumerate(self.layers):
             x = lin(x)

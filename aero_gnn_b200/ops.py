@@ -95,6 +95,25 @@ class _Profile:
 PROFILE = _Profile()
 
 
+class Fallbacks:
+    """Work that left the fused sm_100a kernels for a chain of library (ATen / cuBLAS) ops ON THE GPU, counted and
+    announced once per reason so that it never happens silently.  There is no CPU fallback anywhere; these are the
+    shapes / activations the kernels do not cover: MLP widths other than 128 (models/mlp.py) and activations whose
+    derivative is not a function of their output (SiLU, GELU, ...: processor.eager_stack)."""
+
+    counts: dict = {}
+    _warned: set = set()
+
+    @classmethod
+    def note(cls, reason: str, detail: str) -> None:
+        cls.counts[reason] = cls.counts.get(reason, 0) + 1
+        if reason not in cls._warned:
+            cls._warned.add(reason)
+            import warnings
+            warnings.warn(f"aero_gnn_b200: {detail} -- running a chain of library ops on the GPU instead of the fused "
+                          f"sm_100a kernels (counted in ops.Fallbacks.counts['{reason}'])", RuntimeWarning, stacklevel=3)
+
+
 # ------------------------------------------------------------------------------------------------
 # graph plan
 # ------------------------------------------------------------------------------------------------

@@ -388,8 +388,64 @@ class MGNStackFn(torch.autograd.Function):
         return (None, None, G_x, G_e, *grads)
 
 
+class _SegmentSumFn(torch.autograd.Function):
+    """agg[n] = sum of rows [rowptr[n], rowptr[n+1]) (fp32, CSR order, deterministic); backward = row broadcast."""
+
+    @staticmethod
+    def forward(ctx, e, plan):
+        ctx.plan = plan
+        return ops.segment_reduce(e.contiguous(), plan.rowptr, None, plan.N, out_dtype=torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.gather_rows(g.contiguous(), ctx.plan.dst), None
+
+
+def _unpack_block(w: torch.Tensor, L: int):
+    """(W_main, [(W_l, b_l)...], W_out, b_out, gamma, beta) views of a packed block vector (pack_block layout)."""
+    mats = [w[i * D * D: (i + 1) * D * D].view(D, D) for i in range(L + 2)]
+    v = w[(L + 2) * D * D:]
+    vecs = [v[i * D: (i + 1) * D] for i in range(L + 3)]
+    return mats[0], list(zip(mats[1: L + 1], vecs[:L])), mats[L + 1], vecs[L], vecs[L + 1], vecs[L + 2]
+
+
+def eager_stack(cfg: StackConfig, plan: ops.GraphPlan, x: torch.Tensor, e: torch.Tensor, steps: Sequence[StepWeights]):
+    """The same K processor steps as MGNStackFn as a chain of library ops ON THE GPU with torch autograd, for
+    activations the fused kernels do not cover: they take an activation's derivative from its OUTPUT (relu, tanh,
+    sigmoid, elu, leaky_relu), which SiLU / GELU / ... do not allow.  The reference accepts any torch.nn.functional
+    name (mlp.py:37), so those run here -- announced and counted (ops.Fallbacks), never silently.  Receiver sums stay
+    the deterministic segmented reduction."""
+    import torch.nn.functional as F
+    ops.Fallbacks.note("eager_activation", f"activation '{cfg.act_edge}'/'{cfg.act_node}' has no fused block kernel")
+    fe, fn = getattr(F, cfg.act_edge), getattr(F, cfg.act_node)
+    dt = x.dtype
+    src, dst = plan.src.long(), plan.dst.long()
+
+    def tail(h, act, hidden, w_out, b_out, gamma, beta):
+        for w, b in hidden:
+            h = act(F.linear(h, w.to(dt), b.to(dt)))
+        y = F.linear(h, w_out.to(dt), b_out.to(dt))
+        return F.layer_norm(y, (D,), gamma.to(dt), beta.to(dt), 1e-5) if cfg.use_ln else y
+
+    for s in steps:
+        we, he, woe, boe, ge, be = _unpack_block(s.w_edge, cfg.L_edge)
+        wn, hn, won, bon, gn, bn = _unpack_block(s.w_node, cfg.L_node)
+        P = F.linear(x, s.w_proj, s.b_proj)                                   # [N, 3D]
+        h = fe(F.linear(e, we.to(dt)) + P[:, :D][src] + P[:, D:2 * D][dst])
+        e = e + tail(h, fe, he, woe, boe, ge, be)
+        agg = _SegmentSumFn.apply(e, plan)
+        if cfg.mean:
+            agg = agg * plan.inv_deg[:, None]
+        h = fn(F.linear(agg.to(dt), wn.to(dt)) + P[:, 2 * D:])
+        x = x + tail(h, fn, hn, won, bon, gn, bn)
+    return x, e
+
+
 def run_stack(cfg: StackConfig, plan: ops.GraphPlan, x: torch.Tensor, e_csr: torch.Tensor,
               steps: Sequence[StepWeights]):
+    if cfg.act_edge not in ops._l.ACT_CODES or cfg.act_node not in ops._l.ACT_CODES:
+        ops._require_cuda(x, e_csr)
+        return eager_stack(cfg, plan, x, e_csr, steps)
     flat = []
     for s in steps:
         flat += [s.w_edge, s.w_node, s.w_proj, s.b_proj]

@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from aero_gnn_b200 import lib
-L = lib.load()
+L = lib.load_probe()
 dev = torch.device("cuda", 0)
 g = torch.Generator().manual_seed(0)
 a = torch.randn(128, 128, generator=g).to(dev, torch.bfloat16)

@@ -220,3 +220,15 @@ def test_pack_spec_is_cached_per_module_and_invalidated(monkeypatch):
     twin = copy.deepcopy(layer)
     twin.step_weights(torch.bfloat16)
     assert all(any(b is p for p in twin.parameters()) for b in seen[6].bases)
+
+
+def test_probe_library_is_separate_and_exports_its_header():
+    """The hardware probes live in libaero_probe.so (include/aero_gnn_debug.h), not in the product library."""
+    from aero_gnn_b200 import lib
+    hdr = open(os.path.join(ROOT, "include", "aero_gnn_debug.h")).read()
+    declared = set(re.findall(r"\b(aero_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(lib.PROBE_SIGNATURES)
+    product = lib.load()
+    probe = lib.load_probe()
+    for name in declared:
+        assert hasattr(probe, name) and not hasattr(product, name), name

@@ -283,11 +283,54 @@ def test_gmp_bf16_tcgen05_vs_fp32_oracle():
         assert ours <= max(1e-2, 2.0 * theirs), (name, ours, theirs)
 
 
-def test_gmp_silu_is_rejected_loudly():
+def test_gmp_silu_runs_the_announced_eager_chain_and_matches_the_oracle():
+    """GMP(activation='silu') (the bytecode builds ReLU | SiLU, bistride_ops orig :216): SiLU's derivative is not a
+    function of its output, so the step runs processor.eager_stack -- library ops on the GPU, announced with a
+    RuntimeWarning and counted, never silent -- and must match the oracle like the fused path does."""
     M = _M()
+    from aero_gnn_b200 import ops
+    torch.manual_seed(3)
     mod = M.GMP(128, 128, 128, activation="silu").to(DEV)
-    with pytest.raises(RuntimeError, match="SiLU"):
-        mod(torch.zeros(4, 128, device=DEV), torch.zeros(2, 128, device=DEV), torch.tensor([[0, 1], [1, 2]], device=DEV))
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in mod.state_dict().items()}
+    g = torch.Generator().manual_seed(4)
+    n, e = 700, 4100
+    x, ea = torch.randn(n, 128, generator=g), torch.randn(e, 128, generator=g)
+    ei = _random_graph(n, e, 9)
+    before = ops.Fallbacks.counts.get("eager_activation", 0)
+    xd, ed = x.to(DEV).requires_grad_(True), ea.to(DEV).requires_grad_(True)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        xo, eo = mod(xd, ed, ei.to(DEV))
+    assert ops.Fallbacks.counts["eager_activation"] == before + 1
+    xr, er = x.clone().requires_grad_(True), ea.clone().requires_grad_(True)
+    xref, eref = B.gmp(sd, "", xr, er, ei, activation="silu")
+    assert rel_err(xo, xref) < 1e-5 and rel_err(eo, eref) < 1e-5
+    gx = torch.randn(n, 128, generator=g)
+    xo.backward(gx.to(DEV))
+    names = list(sd)
+    ref = torch.autograd.grad(xref, [xr, er] + [sd[k] for k in names], gx)
+    got = [xd.grad, ed.grad] + [p.grad for _, p in mod.named_parameters()]
+    for name, a, r in zip(["x", "e"] + names, got, ref):
+        assert rel_err(a, r) < 1e-4, (name, rel_err(a, r))
+
+
+def test_processor_layer_with_gelu_runs_the_eager_chain():
+    """The reference takes any torch.nn.functional name (mlp.py:37); one the fused kernels do not cover still works."""
+    import aero_gnn_b200.models as MM
+    import warnings
+    from oracle import mgn_oracle as O
+    torch.manual_seed(1)
+    layer = MM.MeshGraphNetLayer(128, 128, 128, 1, 1, activation_fn="gelu", aggregation="mean").to(DEV)
+    sd = {k: v.detach().cpu() for k, v in layer.state_dict().items()}
+    g = torch.Generator().manual_seed(2)
+    x, ea = torch.randn(300, 128, generator=g), torch.randn(1700, 128, generator=g)
+    ei = _random_graph(300, 1700, 3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        xo, eo = layer(x.to(DEV), ea.to(DEV), ei.to(DEV))
+    xr, er = O.mgn_layer(sd, "", x, ea, ei, "mean", act="gelu")
+    assert rel_err(xo, xr) < 1e-5 and rel_err(eo, er) < 1e-5
 
 
 @pytest.mark.parametrize("levels", [1, 3])

@@ -217,7 +217,7 @@ def test_tmem_layout_probes():
     occupies lanes 32*(r/16) + r%16 (+16 with lane offset 16, so two of them share one column range), and a GEMM whose
     A operand was written to tensor memory with tcgen05.st reproduces a * b^T."""
     from aero_gnn_b200 import lib
-    L = lib.load()
+    L = lib.load_probe()                       # libaero_probe.so: the probes are not in the product library
     dev = torch.device("cuda", 0)
     g = torch.Generator().manual_seed(0)
     a = torch.randn(128, 128, generator=g).to(dev, torch.bfloat16)
