@@ -53,7 +53,8 @@ __global__ void umma_prepare_kernel(const float* __restrict__ w, int L, uint8_t*
 template <bool RELU>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 umma_block_fwd_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_resid,
-                      const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_h0) {
+                      const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_h0,
+                      const __grid_constant__ CUtensorMap tm_mlat) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   const int L = a.L;
@@ -211,6 +212,10 @@ umma_block_fwd_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_main, c
         if (elect_one()) {
           issue_gemm(tacc, a_s, false, w_s + (uint32_t)layer * TILE_BYTES, false, false);
           mma_commit(bar_s);
+          if (layer == 0 && a.main_lat) {   // the staged (scaled, rounded) fp32 rows leave as a latent-dtype copy
+            tma::store_tile(&tm_mlat, a_s, (int)row0);
+            tma::store_commit();
+          }
         }
         __syncwarp();
       }
@@ -234,6 +239,13 @@ umma_block_fwd_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_main, c
         named_sync(bar_id, FWD_GT);
       }
 
+      if (layer == 0 && a.main_lat) {   // the copy-out above has read the tile before the gather below overwrites it
+        if (gw0) {
+          if (elect_one()) tma::store_wait_read();
+          __syncwarp();
+        }
+        named_sync(bar_id, FWD_GT);
+      }
       if (layer == 0) {
         // the MMA that read A has completed: A now receives the coalesced gather P_s[src] + P_d[dst], then each
         // thread turns its (row, chunk) into h0 in place
@@ -453,8 +465,12 @@ int umma_block_fwd(const aero_block_desc* d, cudaStream_t st) {
   int64_t tiles = cdiv(d->rows, 128);
   int64_t want = cdiv(tiles, FWD_GROUPS);
   int grid = (int)(want < sm_count() ? want : sm_count());
-  CUtensorMap tm_main, tm_resid, tm_out, tm_h0;
-  if (tma::make_rows_map(d->out, d->rows, &tm_out) ||
+  CUtensorMap tm_main, tm_resid, tm_out, tm_h0, tm_mlat;
+  if (d->main_lat && !d->main_f32) {
+    set_error("umma_block_fwd: main_lat is the latent-dtype copy of fp32 main rows (main_f32 = 1 only)");
+    return AERO_EINVAL;
+  }
+  if (tma::make_rows_map(d->out, d->rows, &tm_out) || tma::make_rows_map(d->main_lat ? d->main_lat : d->out, d->rows, &tm_mlat) ||
       tma::make_rows_map(d->main_f32 ? d->out : d->main, d->rows, &tm_main) ||
       tma::make_rows_map(d->resid ? d->resid : d->out, d->rows, &tm_resid) ||
       tma::make_rows_map(d->h0 ? d->h0 : d->out, d->rows, &tm_h0)) {
@@ -462,9 +478,9 @@ int umma_block_fwd(const aero_block_desc* d, cudaStream_t st) {
     return AERO_ECUDA;
   }
   if (d->act == AERO_ACT_RELU)
-    umma_block_fwd_kernel<true><<<grid, FWD_THREADS, fwd_smem(d->L), st>>>(a, tm_main, tm_resid, tm_out, tm_h0);
+    umma_block_fwd_kernel<true><<<grid, FWD_THREADS, fwd_smem(d->L), st>>>(a, tm_main, tm_resid, tm_out, tm_h0, tm_mlat);
   else
-    umma_block_fwd_kernel<false><<<grid, FWD_THREADS, fwd_smem(d->L), st>>>(a, tm_main, tm_resid, tm_out, tm_h0);
+    umma_block_fwd_kernel<false><<<grid, FWD_THREADS, fwd_smem(d->L), st>>>(a, tm_main, tm_resid, tm_out, tm_h0, tm_mlat);
   AERO_LAUNCH_CHECK();
   if (d->agg) return launch_agg_fixup(a.agg_part, d->rowptr, d->agg, d->rows, d->n_nodes, 128, d->idx1, st);
   return AERO_OK;

@@ -289,6 +289,16 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
           gp[2 * j + 1] = pack_bf16(bf16_lo(gp[2 * j + 1]) + t4.z, bf16_hi(gp[2 * j + 1]) + t4.w);
         }
       }
+      // ... and, still under the MMA, the part of the LayerNorm backward that does not need y: A = sum g*gamma
+      const float* gam = vec + (L + 1) * 128 + ch * 32;
+      float aa = 0.f, ab = 0.f;
+      if (a.use_ln) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          aa = fmaf(bf16_lo(gp[j]), gam[2 * j], aa);
+          ab = fmaf(bf16_hi(gp[j]), gam[2 * j + 1], ab);
+        }
+      }
       mbar_wait(bar_mma, ph_mma);
       ph_mma ^= 1;
       fence_after_sync();
@@ -302,17 +312,15 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
         v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
       }
       if (a.use_ln) {
-        const float* gam = vec + (L + 1) * 128 + ch * 32;
-        // one pass, four row sums: S1 = sum y, S2 = sum y^2, A = sum g*gamma, B = sum g*gamma*y
-        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f, aa = 0.f, ab = 0.f, ba = 0.f, bb = 0.f;
+        // one pass, three more row sums: S1 = sum y, S2 = sum y^2, B = sum g*gamma*y
+        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f, ba = 0.f, bb = 0.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float ylo = v[2 * j], yhi = v[2 * j + 1];
-          const float wlo = bf16_lo(gp[j]) * gam[2 * j], whi = bf16_hi(gp[j]) * gam[2 * j + 1];
           s1a += ylo; s1b += yhi;
           s2a = fmaf(ylo, ylo, s2a); s2b = fmaf(yhi, yhi, s2b);
-          aa += wlo; ab += whi;
-          ba = fmaf(wlo, ylo, ba); bb = fmaf(whi, yhi, bb);
+          ba = fmaf(bf16_lo(gp[j]) * gam[2 * j], ylo, ba);
+          bb = fmaf(bf16_hi(gp[j]) * gam[2 * j + 1], yhi, bb);
         }
         reinterpret_cast<float4*>(red)[ch * 128 + row] = make_float4(s1a + s1b, s2a + s2b, aa + ab, ba + bb);
         __syncthreads();
@@ -324,8 +332,10 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
         }
         const float mean = S1 * (1.f / 128.f);
         const float rstd = rsqrtf(fmaxf(S2 * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
-        const float m1 = A * (1.f / 128.f);
-        const float m2 = rstd * (B - mean * A) * (1.f / 128.f);   // mean of g*gamma*yhat
+        // dL/dy = rstd * (g*gamma - mean(g*gamma) - yhat * mean(g*gamma*yhat)),  yhat = y*rstd - mean*rstd
+        const float c0 = -mean * rstd;
+        const float c1 = -rstd * A * (1.f / 128.f);
+        const float c2 = -rstd * rstd * (B - mean * A) * (1.f / 128.f);
         float z[32];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
@@ -334,15 +344,17 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
           for (int k = 0; k < 4; ++k) {
             const int j = 4 * jj + k;
             const float glo = bf16_lo(gp[j]), ghi = bf16_hi(gp[j]);
-            const float hlo = (v[2 * j] - mean) * rstd, hhi = (v[2 * j + 1] - mean) * rstd;
-            z[2 * j] = glo * hlo;
+            const float hlo = fmaf(v[2 * j], rstd, c0), hhi = fmaf(v[2 * j + 1], rstd, c0);
+            z[2 * j] = glo * hlo;           // g * yhat: d(gamma) terms
             z[2 * j + 1] = ghi * hhi;
-            op[k] = pack_bf16(rstd * (glo * gam[2 * j] - m1 - hlo * m2), rstd * (ghi * gam[2 * j + 1] - m1 - hhi * m2));
+            op[k] = pack_bf16(fmaf(hlo, c2, fmaf(glo * gam[2 * j], rstd, c1)),
+                              fmaf(hhi, c2, fmaf(ghi * gam[2 * j + 1], rstd, c1)));
           }
           *reinterpret_cast<uint4*>(G + tile_chunk_off(row, ch * 4 + jj)) = make_uint4(op[0], op[1], op[2], op[3]);
         }
         // d(gamma): column sums of z over the warp's 32 rows by a shuffle transpose-reduce (lane l ends with the
-        // sum of column 32*ch + l); fixed order -> deterministic
+        // sum of column 32*ch + l); fixed order -> deterministic.  (Deferring it under the next phase's MMAs was
+        // measured slower: 32 more live registers across the phase boundary.)
 #pragma unroll
         for (int sft = 16; sft >= 1; sft >>= 1) {
           const bool upper = (lane & sft) != 0;

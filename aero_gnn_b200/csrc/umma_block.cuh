@@ -26,6 +26,7 @@ struct UmmaArgs {
   __nv_bfloat16* g_h0;
   float* w_part;
   __nv_bfloat16* h0;   // fwd: optional output; bwd: optional input replacing the layer-0 recompute
+  __nv_bfloat16* main_lat;   // fwd, main_f32: optional bf16 copy of the staged (scaled) main rows
 };
 
 constexpr int UMMA_MAX_L = 2;
@@ -354,6 +355,7 @@ static inline UmmaArgs make_uargs(const aero_block_desc* d) {
   a.prep = reinterpret_cast<const uint8_t*>(d->prepared);
   a.out = reinterpret_cast<__nv_bfloat16*>(d->out);
   a.h0 = reinterpret_cast<__nv_bfloat16*>(d->h0);
+  a.main_lat = reinterpret_cast<__nv_bfloat16*>(d->main_lat);
   a.agg = d->agg; a.agg_part = nullptr;
   a.g_out = reinterpret_cast<const __nv_bfloat16*>(d->g_out);
   a.g_agg = d->g_agg; a.g_main = d->g_main;

@@ -369,7 +369,8 @@ def _desc(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, main
 
 def block_fwd(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, main_scale=None, rowptr=None,
               want_agg=False, kind=None, h0_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-              agg_out: Optional[torch.Tensor] = None, agg_clear: bool = True, rows: Optional[tuple] = None):
+              agg_out: Optional[torch.Tensor] = None, agg_clear: bool = True, rows: Optional[tuple] = None,
+              main_lat_out: Optional[torch.Tensor] = None):
     """Forward of one fused block; returns (out, agg or None).  `h0_out` ([rows,128], latent dtype, tcgen05 path
     only) receives the first hidden activation so that the backward does not have to recompute it.
 
@@ -395,6 +396,8 @@ def block_fwd(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, 
     d.out = out.data_ptr()
     d.agg = agg.data_ptr() if agg is not None else None
     d.h0 = h0_out.data_ptr() if h0_out is not None else None
+    # tcgen05 path, fp32 `main` (node block): latent-dtype copy of the staged rows round(main * main_scale)
+    d.main_lat = main_lat_out.data_ptr() if main_lat_out is not None else None
     if not agg_clear:
         d.flags = _l.AERO_BLOCK_AGG_NO_CLEAR
     if rows is not None:
@@ -437,7 +440,8 @@ def wgrad_into(g_w: torch.Tensor, g_h0: torch.Tensor, rows_in: torch.Tensor) -> 
 def block_bwd(prep: PreparedBlock, main, P, idx0, idx1, poff0, poff1, g_out, *, g_agg=None, main_scale=None,
               has_resid_grad=False, g_main_out: Optional[torch.Tensor] = None, kind=None,
               h0: Optional[torch.Tensor] = None, n_nodes: Optional[int] = None,
-              rowptr: Optional[torch.Tensor] = None, g_w_out: Optional[torch.Tensor] = None):
+              rowptr: Optional[torch.Tensor] = None, g_w_out: Optional[torch.Tensor] = None,
+              main_is_lat_copy: bool = False):
     """Backward of one fused block; returns (g_main, g_h0, g_w_packed[fp32], W_main slot zero).  With `h0` (the
     rows kept by block_fwd(h0_out=...)) layer 0 is not recomputed and `P` may be None.  `rowptr` (receiver CSR of
     the rows, with `g_agg`) lets the TMA-fed kernel take d(beta)'s receiver part as sum_n deg(n) g_agg[n]."""
@@ -456,7 +460,14 @@ def block_bwd(prep: PreparedBlock, main, P, idx0, idx1, poff0, poff1, g_out, *, 
               rowptr=rowptr)
     d.h0 = h0.data_ptr() if h0 is not None else None
     rows = main.size(0)
-    g_main = g_main_out if g_main_out is not None else torch.empty((rows, D), dtype=main.dtype, device=dev)
+    g_main_dtype = main.dtype
+    if main_is_lat_copy:
+        # `main` is the latent-dtype copy block_fwd(main_lat_out=...) made of fp32 rows (node block: the aggregate);
+        # with kept h_0 rows the kernel does not read `main` at all, but the gradient w.r.t. the fp32 rows is fp32
+        if h0 is None:
+            raise RuntimeError("block_bwd: main_is_lat_copy needs the kept h_0 rows")
+        d.main_f32, g_main_dtype = 1, torch.float32
+    g_main = g_main_out if g_main_out is not None else torch.empty((rows, D), dtype=g_main_dtype, device=dev)
     g_h0 = torch.empty((rows, D), dtype=ldt, device=dev)
     # every slot except W_main is written by the kernel (W_main: by the caller's wgrad_into); `g_w_out` lets a
     # stack place the packed gradient inside one flat buffer (one all-reduce, no per-parameter copies)

@@ -247,10 +247,12 @@ class PartitionedStackFn(torch.autograd.Function):
             # x' goes straight into the own rows of the next step's extended row matrix
             x_next = x.new_empty((plan.N, D)) if k + 1 < K else None
             out_rows = x_next[:n_own] if x_next is not None else None
+            agg_lat = torch.empty_like(x) if (keep_h0 and dt != torch.float32) else None
             x_new, _ = ops.block_fwd(pn, agg, x_cur, P, None, None, 2 * D, 0, main_scale=scale, kind="node_fwd",
-                                     h0_out=h0n, out=out_rows)
-            # x_ext and (h_0 of both blocks | P) are kept so the backward needs no second halo exchange
-            saved += [x_ext, e, agg, h0e, h0n] if keep_h0 else [x_ext, e, agg, P, P]
+                                     h0_out=h0n, out=out_rows, main_lat_out=agg_lat)
+            # x_ext and (h_0 of both blocks | P) are kept so the backward needs no second halo exchange; with kept h_0
+            # the aggregate is kept as the latent-dtype copy the node kernel made of its staged rows
+            saved += [x_ext, e, agg_lat if agg_lat is not None else agg, h0e, h0n] if keep_h0 else [x_ext, e, agg, P, P]
             e = e_new
             if x_next is not None:
                 x_ext = x_next
@@ -286,10 +288,14 @@ class PartitionedStackFn(torch.autograd.Function):
             else:
                 pe = ops.PreparedBlock(w_edge, cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
                 pn = ops.PreparedBlock(w_node, cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
+            lat = ctx.keep_h0 and agg.dtype != torch.float32
             g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale, kind="node_bwd",
-                                               h0=h0n, n_nodes=plan.N, g_w_out=sink.w_node(k))
-            agg_eff = agg if scale is None else agg * scale[:, None]
-            ops.wgrad_into(g_wn, g_h0n, agg_eff.to(dt))
+                                               h0=h0n, n_nodes=plan.N, g_w_out=sink.w_node(k), main_is_lat_copy=lat)
+            if lat:
+                ops.wgrad_into(g_wn, g_h0n, agg)
+            else:
+                agg_eff = agg if scale is None else agg * scale[:, None]
+                ops.wgrad_into(g_wn, g_h0n, agg_eff.to(dt))
             G_e, g_h0e, g_we = ops.block_bwd(pe, e, P, plan.src, plan.dst, 0, D, G_e, g_agg=g_agg, has_resid_grad=True,
                                              g_main_out=G_e, kind="edge_bwd", h0=h0e, n_nodes=plan.N,
                                              rowptr=plan.rowptr, g_w_out=sink.w_edge(k))

@@ -325,11 +325,14 @@ class MGNStackFn(torch.autograd.Function):
             h0n = torch.empty_like(x) if keep_h0 else None
             e_new, agg = ops.block_fwd(pe, e, e, P, plan.src, plan.dst, 0, D, rowptr=plan.rowptr, want_agg=True,
                                        kind="edge_fwd", h0_out=h0e)
+            # tcgen05 path: the node kernel also stores the rows its first GEMM consumed, round(agg * scale) in the
+            # latent dtype -- what the backward's weight-gradient GEMM needs -- and the fp32 aggregate is not kept
+            agg_lat = torch.empty_like(x) if (keep_h0 and x.dtype != torch.float32) else None
             x_new, _ = ops.block_fwd(pn, agg, x, P, None, None, 2 * D, 0, main_scale=scale, kind="node_fwd",
-                                     h0_out=h0n)
+                                     h0_out=h0n, main_lat_out=agg_lat)
             # tcgen05 path: the first hidden activation of both blocks is kept (the backward then skips one gather,
             # one GEMM and one epilogue per tile and never reads P); CUDA-core path: P is kept and layer 0 recomputed
-            saved += [x, e, agg, h0e, h0n] if keep_h0 else [x, e, agg, P, P]
+            saved += [x, e, agg_lat if agg_lat is not None else agg, h0e, h0n] if keep_h0 else [x, e, agg, P, P]
             x, e = x_new, e_new
         ctx.cfg, ctx.plan, ctx.K = cfg, plan, K
         ctx.set_materialize_grads(False)
@@ -361,10 +364,15 @@ class MGNStackFn(torch.autograd.Function):
                 pe = ops.PreparedBlock(w_edge, cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
                 pn = ops.PreparedBlock(w_node, cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
             # node block: g_agg, gradient of the node pre-activation, MLP weight grads
+            lat = ctx.keep_h0 and agg.dtype != torch.float32      # agg = latent-dtype copy of the scaled aggregate
             g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale,
-                                               kind="node_bwd", h0=h0n, n_nodes=plan.N, g_w_out=sink.w_node(k))
-            agg_eff = agg if scale is None else agg * scale[:, None]
-            ops.wgrad_into(g_wn, g_h0n, agg_eff.to(dt))
+                                               kind="node_bwd", h0=h0n, n_nodes=plan.N, g_w_out=sink.w_node(k),
+                                               main_is_lat_copy=lat)
+            if lat:
+                ops.wgrad_into(g_wn, g_h0n, agg)
+            else:
+                agg_eff = agg if scale is None else agg * scale[:, None]
+                ops.wgrad_into(g_wn, g_h0n, agg_eff.to(dt))
             # edge block: total gradient of e' = G_e + g_agg[receiver]
             G_e, g_h0e, g_we = ops.block_bwd(pe, e, P, plan.src, plan.dst, 0, D, G_e, g_agg=g_agg,
                                              has_resid_grad=True, g_main_out=G_e, kind="edge_bwd", h0=h0e,

@@ -196,6 +196,10 @@ typedef struct aero_block_desc {
    * of recomputing it (main, P and idx0 are then not read and P may be NULL; the trade is +256 B/row kept from
    * the forward for one GEMM, one gather and one epilogue less per backward tile).  AERO_PATH_UMMA only. */
   void* h0;
+  /* fwd, optional, AERO_PATH_UMMA with main_f32: [rows,128] latent-dtype copy of the rows the first GEMM consumed,
+   * i.e. round(main[r] * main_scale[r]) -- the node block's (scaled) aggregate in the latent dtype, which the caller's
+   * weight-gradient GEMM  g_h0^T @ main  needs (saves a separate cast / scale pass over the fp32 aggregate). */
+  void* main_lat;
 } aero_block_desc;
 
 size_t aero_block_prepared_bytes(int L, int path);
