@@ -319,6 +319,30 @@ class PartitionedStackFn(torch.autograd.Function):
         return (None, None, G_x, G_e, *grads)
 
 
+class HaloExtendFn(torch.autograd.Function):
+    """x_ext = [own rows (local order) | halo rows fetched from their owners]; the backward returns the halo rows'
+    gradients to the owners and adds them there (deterministic order).  Lets any 1-hop operator that works on a whole
+    graph -- WeightedEdgeConv of the BFS-bistride variant, SURVEY.md 8(e) row 3 -- run on a rank's local graph."""
+
+    @staticmethod
+    def forward(ctx, part: "PartitionedProcessor", x_own: torch.Tensor):
+        ex, n_own = part.exchanger, part.n_own
+        x_ext = x_own.new_empty((part.plan.N, x_own.size(1)))
+        x_ext[:n_own].copy_(x_own)
+        ex.forward_finish(ex.forward_start(x_ext, out=x_ext[n_own:]))
+        ctx.part = part
+        return x_ext
+
+    @staticmethod
+    def backward(ctx, g_ext):
+        part = ctx.part
+        n_own = part.n_own
+        g_ext = g_ext.contiguous()
+        g_own = g_ext[:n_own].clone()
+        part.exchanger.backward(g_ext[n_own:], g_own)
+        return None, g_own
+
+
 class PartitionedProcessor:
     """Receiver-block partition of one mesh for this rank: halo plan, local graph plan, exchange, grad all-reduce."""
 
@@ -376,6 +400,34 @@ class PartitionedProcessor:
             self._stack_params.update(id(p) for p in layer.parameters())
         x, e = PartitionedStackFn.apply(cfg, self, self.to_local(x_own), e_csr, *flat)
         return self.to_global(x), e
+
+    # ---- GMP / WeightedEdgeConv variant on the partition (SURVEY.md 8(e) row 3) ------------------------------
+    def extend(self, x_own_local: torch.Tensor) -> torch.Tensor:
+        """[n_local, w]: own rows (LOCAL order) followed by the halo rows of their owners; differentiable."""
+        return HaloExtendFn.apply(self, x_own_local.contiguous())
+
+    def extend_static(self, t_own_global_order: torch.Tensor) -> torch.Tensor:
+        """Per-node data that does not change during training (positions): exchanged ONCE per mesh, no gradient."""
+        with torch.no_grad():
+            loc = t_own_global_order[self.own_order.long()].contiguous()
+            return HaloExtendFn.apply(self, loc)
+
+    @property
+    def local_edge_index(self) -> torch.Tensor:
+        """[2, E_loc] int64 local (sender, receiver) ids in the order of halo.edge_ids (ascending global edge id)."""
+        if not hasattr(self, "_local_ei"):
+            self._local_ei = torch.from_numpy(self.halo.local_edge_index).to(self.plan.rowptr.device)
+        return self._local_ei
+
+    def weighted_edge_conv(self, conv, x_own: torch.Tensor, pos_ext: torch.Tensor, edge_weights=None,
+                           compute_weights: bool = True):
+        """WeightedEdgeConv.forward on this rank's block: x_own in ascending global id, pos_ext from extend_static().
+        Returns (out for the own nodes in ascending global id, edge weights of the local edges in halo.edge_ids order).
+        Every incoming edge of an own node is local, so the own rows are exact; gradients of halo rows travel back to
+        their owners through HaloExtendFn; the module's weight gradients are per-rank partials (allreduce_grads)."""
+        x_ext = self.extend(self.to_local(x_own))
+        out, w = conv(x_ext, self.local_edge_index, pos_ext, edge_weights=edge_weights, compute_weights=compute_weights)
+        return self.to_global(out[: self.n_own]), w
 
     def allreduce_grads(self, params) -> None:
         """Sum the gradients of parameters used OUTSIDE run() (encoders, decoder) over the ranks with one flat

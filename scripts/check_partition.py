@@ -55,6 +55,41 @@ errs["g_w"] = max(rel(p.grad, r) for p, r in zip(net.layers.parameters(), ref_gw
 errs["interior_edges"] = pp.E_int / max(pp.E_loc, 1)
 bad = {k: v for k, v in errs.items() if k != "interior_edges" and not v < tol}
 print(f"rank {rank}/{world} dtype {dt} n_own {pp.n_own} n_halo {pp.halo.n_halo} E_loc {pp.E_loc} errs {errs}", flush=True)
+
+# ---- GMP / WeightedEdgeConv variant (BFS-bistride operators) on the same partition ------------------------------
+if dt == torch.float32:
+    torch.manual_seed(1)
+    gmps = torch.nn.ModuleList(M.GMP(128, 128, 128) for _ in range(2)).to(dev)
+    conv = M.WeightedEdgeConv(128, 128).to(dev)
+    pos = mesh.pos[:, :2].clone() + 1e-3 * torch.rand(N, 2, generator=torch.Generator().manual_seed(3))
+    ei_d = mesh.edge_index.to(dev)
+    # single GPU
+    x0 = xg.to(dev).requires_grad_(True)
+    e0 = eg.to(dev).requires_grad_(True)
+    x, e = x0, e0
+    for m_ in gmps:
+        x, e = m_(x, e, ei_d)
+    oc, wc = conv(x, ei_d, pos.to(dev))
+    (oc * probe.to(dev)).sum().backward()
+    ref2 = dict(out=oc.detach(), w=wc.detach(), gx=x0.grad.clone(), ge=e0.grad.clone(),
+                gw=[p.grad.clone() for p in list(gmps.parameters()) + list(conv.parameters())])
+    for p in list(gmps.parameters()) + list(conv.parameters()):
+        p.grad = None
+    # partitioned: GMP stack through pp.run, WeightedEdgeConv on the halo-extended rows, positions exchanged once
+    pos_ext = pp.extend_static(pos[pp.lo:pp.hi].to(dev))
+    x1 = xg[pp.lo:pp.hi].to(dev).requires_grad_(True)
+    e1 = eg.to(dev)[ids].requires_grad_(True)
+    xo2, _ = pp.run(gmps, x1, e1)
+    oc2, wc2 = pp.weighted_edge_conv(conv, xo2, pos_ext)
+    (oc2 * probe[pp.lo:pp.hi].to(dev)).sum().backward()
+    others = list(conv.parameters())
+    pp.allreduce_grads(others)
+    eids = torch.from_numpy(pp.halo.edge_ids).to(dev)
+    errs2 = {"wec_out": rel(oc2, ref2["out"][pp.lo:pp.hi]), "wec_w": rel(wc2, ref2["w"][eids]),
+             "g_x": rel(x1.grad, ref2["gx"][pp.lo:pp.hi]), "g_e": rel(e1.grad, ref2["ge"][ids]),
+             "g_w": max(rel(p.grad, r) for p, r in zip(list(gmps.parameters()) + others, ref2["gw"]))}
+    print(f"rank {rank}/{world} GMP+WeightedEdgeConv on the partition: {errs2}", flush=True)
+    bad.update({"gmp_" + k: v for k, v in errs2.items() if not v < 1e-4})
 t = torch.tensor([len(bad)], device=dev)
 dist.all_reduce(t)
 dist.destroy_process_group()

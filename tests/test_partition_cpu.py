@@ -96,6 +96,16 @@ def _worker(rank, world, port, ei, n, out):
         g2 += 0.0
         ex.backward_finish(tok, g2)
         ok_b = ok_b and torch.equal(g2, expect)
+        # HaloExtendFn (GMP / WeightedEdgeConv variant): extended rows forward, halo gradients back to their owners
+        import types
+        from aero_gnn_b200.partition import HaloExtendFn
+        part = types.SimpleNamespace(exchanger=ex, n_own=pl.n_own, plan=types.SimpleNamespace(N=pl.n_local))
+        xl = x_loc.clone().requires_grad_(True)
+        xe = HaloExtendFn.apply(part, xl)
+        ok_f = ok_f and torch.equal(xe[pl.n_own:], xg[torch.from_numpy(pl.halo_global)]) and torch.equal(xe[:pl.n_own], x_loc)
+        wgt = torch.cat([torch.full((pl.n_own, 4), 0.5), torch.full((pl.n_halo, 4), float(rank + 1))])
+        (xe * wgt).sum().backward()
+        ok_b = ok_b and torch.equal(xl.grad, expect + 0.5)
         out[rank] = (ok_f, ok_b, pl.n_halo)
     finally:
         dist.destroy_process_group()
