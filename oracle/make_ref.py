@@ -22,7 +22,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = os.environ.get("AERO_REFERENCE_ROOT", "/root/reference")
 DST = os.path.join(HERE, "_ref")
 FILES = ["models/mlp.py", "models/mgnLayer.py", "models/mgn.py", "models/bsms_mgn.py", "models/poolmgn.py",
-         "models/fouriermgn.py", "config.yaml"]
+         "models/fouriermgn.py", "config.yaml",
+         # the callers, for the "train.py runs unchanged on the drop-in models" demonstration (scripts/run_reference_train.py)
+         "train.py", "utils.py", "dataset.py", "inference.py"]
 
 
 def make_ref(verbose: bool = True) -> bool:
