@@ -129,9 +129,26 @@ class BistrideCache:
     def __init__(self, capacity: int = 64):
         self.capacity = capacity
         self._d: "OrderedDict[tuple, BistrideLevel]" = OrderedDict()
+        self._last: dict = {}
 
     def get(self, edge_index: torch.Tensor, num_nodes: int, pos: Optional[torch.Tensor]) -> BistrideLevel:
-        key = (_hash_any(edge_index), _hash_any(pos), int(num_nodes), tuple(edge_index.shape), str(edge_index.device))
+        # fast path: the same live tensors at the same version (no hashing kernels, no host read-back)
+        from .pooling import _ident, _same
+        slot = (int(num_nodes), int(edge_index.shape[1]))
+        last = self._last.get(slot)
+        if _same(last, (edge_index, pos), int(num_nodes)):
+            return last[3]
+        lvl = self._get_slow(edge_index, num_nodes, pos)
+        refs, fp = _ident(edge_index, pos)
+        if refs is not None:
+            if len(self._last) > 32:
+                self._last.clear()
+            self._last[slot] = (refs, fp, int(num_nodes), lvl)
+        return lvl
+
+    def _get_slow(self, edge_index: torch.Tensor, num_nodes: int, pos: Optional[torch.Tensor]) -> BistrideLevel:
+        key = (ops.content_key(edge_index), ops.content_key(pos), int(num_nodes), tuple(edge_index.shape),
+               str(edge_index.device))
         lvl = self._d.get(key)
         if lvl is None:
             plan = ops.PLAN_CACHE.get(edge_index, num_nodes)
@@ -148,6 +165,7 @@ class BistrideCache:
 
     def clear(self) -> None:
         self._d.clear()
+        self._last.clear()
 
 
 BISTRIDE_CACHE = BistrideCache()

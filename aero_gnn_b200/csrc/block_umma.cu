@@ -54,7 +54,8 @@ template <bool RELU>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 umma_block_fwd_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_resid,
                       const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_h0,
-                      const __grid_constant__ CUtensorMap tm_mlat) {
+                      const __grid_constant__ CUtensorMap tm_mlat, const __grid_constant__ CUtensorMap tm_h1,
+                      const __grid_constant__ CUtensorMap tm_h2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   const int L = a.L;
@@ -219,10 +220,12 @@ umma_block_fwd_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_main, c
         }
         __syncwarp();
       }
-      if (layer == 1 && a.h0 && gw0) {
-        // keep h_0 for the backward: a TMA store reads the tile while GEMM 1 does
+      // keep h_0 (and, under the keep-all policy, H_1 / H_2) for the backward: a TMA store reads the activation tile
+      // while the GEMM that consumes it does
+      const bool keep_this = layer >= 1 && (layer == 1 ? a.h0 != nullptr : (layer <= 3 && a.hh[layer - 2] != nullptr));
+      if (keep_this && gw0) {
         if (elect_one()) {
-          tma::store_tile(&tm_h0, a_s, (int)row0);
+          tma::store_tile(layer == 1 ? &tm_h0 : (layer == 2 ? &tm_h1 : &tm_h2), a_s, (int)row0);
           tma::store_commit();
         }
         __syncwarp();
@@ -230,7 +233,7 @@ umma_block_fwd_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_main, c
       mbar_wait(bar_s, phase);
       phase ^= 1;
       fence_after_sync();
-      if (layer == 1 && a.h0) {
+      if (keep_this) {
         // the next epilogue overwrites the tile: behind the store's reads (long finished; the barrier is the hand-off)
         if (gw0) {
           if (elect_one()) tma::store_wait_read();
@@ -465,7 +468,16 @@ int umma_block_fwd(const aero_block_desc* d, cudaStream_t st) {
   int64_t tiles = cdiv(d->rows, 128);
   int64_t want = cdiv(tiles, FWD_GROUPS);
   int grid = (int)(want < sm_count() ? want : sm_count());
-  CUtensorMap tm_main, tm_resid, tm_out, tm_h0, tm_mlat;
+  CUtensorMap tm_main, tm_resid, tm_out, tm_h0, tm_mlat, tm_h1, tm_h2;
+  if ((d->h_hidden[0] || d->h_hidden[1]) && !(d->L == 2 && d->h0 && d->h_hidden[0] && d->h_hidden[1])) {
+    set_error("umma_block_fwd: h_hidden needs L == 2, h0 and both of H_1, H_2");
+    return AERO_EINVAL;
+  }
+  if (tma::make_rows_map(d->h_hidden[0] ? d->h_hidden[0] : d->out, d->rows, &tm_h1) ||
+      tma::make_rows_map(d->h_hidden[1] ? d->h_hidden[1] : d->out, d->rows, &tm_h2)) {
+    set_error("umma_block_fwd: cuTensorMapEncodeTiled failed (h_hidden)");
+    return AERO_ECUDA;
+  }
   if (d->main_lat && !d->main_f32) {
     set_error("umma_block_fwd: main_lat is the latent-dtype copy of fp32 main rows (main_f32 = 1 only)");
     return AERO_EINVAL;
@@ -478,9 +490,9 @@ int umma_block_fwd(const aero_block_desc* d, cudaStream_t st) {
     return AERO_ECUDA;
   }
   if (d->act == AERO_ACT_RELU)
-    umma_block_fwd_kernel<true><<<grid, FWD_THREADS, fwd_smem(d->L), st>>>(a, tm_main, tm_resid, tm_out, tm_h0, tm_mlat);
+    umma_block_fwd_kernel<true><<<grid, FWD_THREADS, fwd_smem(d->L), st>>>(a, tm_main, tm_resid, tm_out, tm_h0, tm_mlat, tm_h1, tm_h2);
   else
-    umma_block_fwd_kernel<false><<<grid, FWD_THREADS, fwd_smem(d->L), st>>>(a, tm_main, tm_resid, tm_out, tm_h0, tm_mlat);
+    umma_block_fwd_kernel<false><<<grid, FWD_THREADS, fwd_smem(d->L), st>>>(a, tm_main, tm_resid, tm_out, tm_h0, tm_mlat, tm_h1, tm_h2);
   AERO_LAUNCH_CHECK();
   if (d->agg) return launch_agg_fixup(a.agg_part, d->rowptr, d->agg, d->rows, d->n_nodes, 128, d->idx1, st);
   return AERO_OK;

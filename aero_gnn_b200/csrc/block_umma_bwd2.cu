@@ -85,10 +85,14 @@ __device__ __forceinline__ void mask_epilogue_chunk(uint32_t taddr, uint8_t* Ht,
   }
 }
 
-template <bool RELU>
+// KEPT: the forward also kept H_1 .. H_L (aero_block_desc.h_hidden, L == 2): they are fetched by the TMA engine like
+// h_0 and the recompute of the hidden layers disappears -- two GEMM phases and two epilogues per tile less, for
+// +256 B/row/layer kept from the forward and read here.
+template <bool RELU, bool KEPT>
 __global__ void __launch_bounds__(B2_THREADS, 1)
 umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, const __grid_constant__ CUtensorMap tm_gout,
-                       const __grid_constant__ CUtensorMap tm_gh0, const __grid_constant__ CUtensorMap tm_gmain) {
+                       const __grid_constant__ CUtensorMap tm_gh0, const __grid_constant__ CUtensorMap tm_gmain,
+                       const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_h2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   const int L = a.L;
@@ -96,8 +100,8 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
   uint8_t* X = Wslot + 2 * TILE_BYTES;                      // 4 activation tiles, roles rotate
   float* vec = reinterpret_cast<float*>(X + (size_t)4 * TILE_BYTES);
   float* red = vec + (UMMA_MAX_L_BWD + 3) * 128;             // [4 chunks][128 rows] float4 (LayerNorm row sums)
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 2048);  // [0] mma, [1..2] weight slots, [3] h0, [4] g_out, [5] reload, [6] dW
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 7);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 2048);  // [0] mma, [1..2] weight slots, [3] h0, [4] g_out, [5] reload, [6] dW, [7] h1, [8] h2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 9);
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int q = wid & 3;         // TMEM lane quarter
@@ -108,7 +112,7 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
     for (int i = tid; i < (L + 3) * 128; i += B2_THREADS) vec[i] = vs[i];
   }
   if (tid == 0) {
-    for (int i = 0; i < 7; ++i) mbar_init(smem_u32(&mbar[i]), 1);
+    for (int i = 0; i < 9; ++i) mbar_init(smem_u32(&mbar[i]), 1);
     fence_mbar_init();
   }
   if (tid < 32) tmem_alloc<512>(tmem_slot);
@@ -119,6 +123,7 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
   const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32);
   const uint32_t bar_mma = smem_u32(&mbar[0]);
   const uint32_t bar_h0 = smem_u32(&mbar[3]), bar_g = smem_u32(&mbar[4]), bar_r = smem_u32(&mbar[5]), bar_dw = smem_u32(&mbar[6]);
+  const uint32_t bar_h1 = smem_u32(&mbar[7]), bar_h2 = smem_u32(&mbar[8]);
   const uint32_t x_s = smem_u32(X);
   const uint32_t w_s = smem_u32(Wslot);
   const int act = RELU ? AERO_ACT_RELU : a.act;
@@ -173,12 +178,25 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
         tma::load_tile(x_s + (uint32_t)pH0 * TILE_BYTES, &tm_h0, r0, bar_h0);
         mbar_expect_tx(bar_g, TILE_BYTES);
         tma::load_tile(x_s + (uint32_t)pG * TILE_BYTES, &tm_gout, r0, bar_g);
+        if (KEPT) {
+          mbar_expect_tx(bar_h2, TILE_BYTES);
+          tma::load_tile(x_s + (uint32_t)pH2 * TILE_BYTES, &tm_h2, r0, bar_h2);
+          mbar_expect_tx(bar_h1, TILE_BYTES);
+          tma::load_tile(x_s + (uint32_t)pH1 * TILE_BYTES, &tm_h1, r0, bar_h1);
+        }
       }
       __syncwarp();
     }
-    prefetch(1);
-    prefetch(2);   // L >= 1: matrix 2 exists (W_2 or W_out)
+    if (KEPT) {
+      prefetch(L + 1);   // W_out: output GEMM and the first backward phase; W_2 follows in the other slot
+      prefetch(L);
+    } else {
+      prefetch(1);
+      prefetch(2);   // L >= 1: matrix 2 exists (W_2 or W_out)
+    }
   }
+  bool h_posted = true;   // KEPT: this tile's H_1 / H_0 loads are already in flight (first tile: posted above)
+  uint32_t ph_h1 = 0, ph_h2 = 0;
 
   uint32_t ph_mma = 0, ph_h0 = 0, ph_g = 0, ph_r = 0, ph_dw = 0;
   bool first_tile = true;
@@ -214,6 +232,18 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
         mbar_expect_tx(bar_r, TILE_BYTES);
         tma::load_tile(x_s + (uint32_t)pG * TILE_BYTES, &tm_gout, (int)row0, bar_r);
       }
+      if (KEPT) {
+        // the next tile starts with its incoming gradient and H_2 resident: they go to the tiles phases 2 and 1 free
+        if (done == L && has_next) {
+          mbar_expect_tx(bar_g, TILE_BYTES);
+          tma::load_tile(x_s + (uint32_t)pH2 * TILE_BYTES, &tm_gout, next_r0, bar_g);
+        }
+        if (done == 1 && has_next) {
+          mbar_expect_tx(bar_h2, TILE_BYTES);
+          tma::load_tile(x_s + (uint32_t)pH1 * TILE_BYTES, &tm_h2, next_r0, bar_h2);
+        }
+        return;
+      }
       if (done == L && has_next) {       // next tile's h_0 rows: H_L's tile (L == 2) or the spare (L == 1)
         mbar_expect_tx(bar_h0, TILE_BYTES);
         tma::load_tile(x_s + (uint32_t)pH2 * TILE_BYTES, &tm_h0, next_r0, bar_h0);
@@ -224,18 +254,42 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
       }
     };
 
-    mbar_wait(bar_h0, ph_h0);
-    ph_h0 ^= 1;
+    if (KEPT) {
+      // this tile's H_1 and H_0 rows go to the two tiles the previous tile's output stores are leaving (needed two and
+      // three phases from now); its gradient rows and H_2 were fetched while the previous tile computed
+      if (w0) {
+        if (elect_one() && !h_posted) {
+          tma::store_wait_read();
+          mbar_expect_tx(bar_h1, TILE_BYTES);
+          tma::load_tile(x_s + (uint32_t)pH1 * TILE_BYTES, &tm_h1, (int)row0, bar_h1);
+          mbar_expect_tx(bar_h0, TILE_BYTES);
+          tma::load_tile(x_s + (uint32_t)pH0 * TILE_BYTES, &tm_h0, (int)row0, bar_h0);
+        }
+        __syncwarp();
+      }
+      h_posted = false;
+      mbar_wait(bar_h2, ph_h2);
+      ph_h2 ^= 1;
+      mbar_wait(bar_g, ph_g);
+      ph_g ^= 1;
+    } else {
+      mbar_wait(bar_h0, ph_h0);
+      ph_h0 ^= 1;
+    }
     if (w0 && has_next) {   // pull the next tile's rows into L2 now; the loads above then hit L2
       if (elect_one()) {
         tma::prefetch_tile_l2(&tm_h0, next_r0);
         tma::prefetch_tile_l2(&tm_gout, next_r0);
+        if (KEPT) {
+          tma::prefetch_tile_l2(&tm_h1, next_r0);
+          tma::prefetch_tile_l2(&tm_h2, next_r0);
+        }
       }
       __syncwarp();
     }
 
     // ---- forward recompute of layers 1..L (hidden) ----
-    for (int m = 1; m <= L; ++m) {
+    for (int m = 1; m <= (KEPT ? 0 : L); ++m) {
       if (w0) {
         uint32_t wa = acquire(m);
         fence_after_sync();
@@ -273,7 +327,9 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
           mma_commit(bar_mma);
         }
         __syncwarp();
+        if (KEPT) prefetch(L);   // W_2 into the other slot (held W_main, consumed by the previous tile's last GEMM)
       }
+      if (KEPT) colsum_mma(G, wid, lane, dbet0, dbet1);   // d(beta) part 1 = column sums of the incoming gradient rows
       // under the MMA: this thread's 32 incoming gradient values (4 x 16 B of the G tile) + receiver gradient piece
       uint32_t gp[16];
 #pragma unroll
@@ -379,6 +435,15 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
     for (int m = L + 1; m >= 1; --m) {
       const int tg = (m == L + 1) ? pG : tile_of_h(m);       // tile holding G_m
       const int th = tile_of_h(m - 1);                        // tile holding H_{m-1}, receives G_{m-1}
+      if (KEPT && m <= L) {   // H_{m-1} of this tile has landed (H_L was awaited at the top)
+        if (m == 2) {
+          mbar_wait(bar_h1, ph_h1);
+          ph_h1 ^= 1;
+        } else {
+          mbar_wait(bar_h0, ph_h0);
+          ph_h0 ^= 1;
+        }
+      }
       if (w0) {
         uint32_t wa = acquire(m);
         fence_after_sync();
@@ -433,7 +498,10 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
       mbar_wait(bar_mma, ph_mma);
       ph_mma ^= 1;
       fence_after_sync();
-      if (w0 && has_next) prefetch(2);   // slot 0 held W_main, just consumed: the next tile's second matrix
+      if (w0 && has_next) {
+        if (KEPT) prefetch(L + 1);   // slot 1 held W_1 (consumed by phase 1): the next tile's W_out
+        else prefetch(2);            // slot 0 held W_main, just consumed: the next tile's second matrix
+      }
       uint8_t* O = X + (size_t)pG * TILE_BYTES;
       if (resid) {
         mbar_wait(bar_r, ph_r);
@@ -480,6 +548,14 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
     // ---- rotate the tile roles: the next tile's inputs are (being) loaded into the tiles freed above ----
     {
       const int oH0 = pH0, oH1 = pH1, oH2 = pH2, oG = pG;
+      if (KEPT) {
+        pG = oH2;    // next incoming gradient rows (posted after phase 2)
+        pH2 = oH1;   // next H_2 rows (posted after phase 1)
+        pH1 = oG;    // next H_1 rows: posted at the top of the next tile, once the g_main store has read the tile
+        pH0 = oH0;   // next h_0 rows: likewise after the g_h0 store
+        first_tile = false;
+        continue;
+      }
       pH0 = oH2;   // next h_0 rows
       pG = oH1;    // next incoming gradient rows
       pH1 = oG;    // written by the next tile's first epilogue, after the g_main store has read it
@@ -566,7 +642,7 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
 
 // ---- host side ------------------------------------------------------------------------------------
 static size_t bwd2_smem() {
-  return 1024 + (size_t)6 * TILE_BYTES + (size_t)(UMMA_MAX_L_BWD + 3) * 512 + 8192 + 7 * 8 + 16;
+  return 1024 + (size_t)6 * TILE_BYTES + (size_t)(UMMA_MAX_L_BWD + 3) * 512 + 8192 + 9 * 8 + 16;
 }
 
 bool umma_bwd2_applicable(const aero_block_desc* d) {
@@ -577,8 +653,11 @@ bool umma_bwd2_applicable(const aero_block_desc* d) {
 }
 
 int umma_block_bwd2(const aero_block_desc* d, UmmaArgs a, int grid, cudaStream_t st) {
-  CUtensorMap tm_h0, tm_gout, tm_gh0, tm_gmain;
-  if (tma::make_rows_map(d->h0, d->rows, &tm_h0) || tma::make_rows_map(d->g_out, d->rows, &tm_gout) ||
+  CUtensorMap tm_h0, tm_gout, tm_gh0, tm_gmain, tm_h1, tm_h2;
+  const bool kept = d->L == 2 && d->h_hidden[0] && d->h_hidden[1];
+  if (tma::make_rows_map(kept ? d->h_hidden[0] : d->h0, d->rows, &tm_h1) ||
+      tma::make_rows_map(kept ? d->h_hidden[1] : d->h0, d->rows, &tm_h2) ||
+      tma::make_rows_map(d->h0, d->rows, &tm_h0) || tma::make_rows_map(d->g_out, d->rows, &tm_gout) ||
       tma::make_rows_map(d->g_h0, d->rows, &tm_gh0) ||
       tma::make_rows_map(d->main_f32 ? d->g_out : d->g_main, d->rows, &tm_gmain)) {
     set_error("umma_block_bwd2: cuTensorMapEncodeTiled failed");
@@ -588,14 +667,20 @@ int umma_block_bwd2(const aero_block_desc* d, UmmaArgs a, int grid, cudaStream_t
   int dev = 0;
   AERO_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    AERO_CUDA(cudaFuncSetAttribute(umma_block_bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd2_smem()));
-    AERO_CUDA(cudaFuncSetAttribute(umma_block_bwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd2_smem()));
+    AERO_CUDA(cudaFuncSetAttribute(umma_block_bwd2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd2_smem()));
+    AERO_CUDA(cudaFuncSetAttribute(umma_block_bwd2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd2_smem()));
+    AERO_CUDA(cudaFuncSetAttribute(umma_block_bwd2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd2_smem()));
+    AERO_CUDA(cudaFuncSetAttribute(umma_block_bwd2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd2_smem()));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  if (d->act == AERO_ACT_RELU)
-    umma_block_bwd2_kernel<true><<<grid, B2_THREADS, bwd2_smem(), st>>>(a, tm_h0, tm_gout, tm_gh0, tm_gmain);
-  else
-    umma_block_bwd2_kernel<false><<<grid, B2_THREADS, bwd2_smem(), st>>>(a, tm_h0, tm_gout, tm_gh0, tm_gmain);
+  const bool relu = d->act == AERO_ACT_RELU;
+  if (kept) {
+    if (relu) umma_block_bwd2_kernel<true, true><<<grid, B2_THREADS, bwd2_smem(), st>>>(a, tm_h0, tm_gout, tm_gh0, tm_gmain, tm_h1, tm_h2);
+    else umma_block_bwd2_kernel<false, true><<<grid, B2_THREADS, bwd2_smem(), st>>>(a, tm_h0, tm_gout, tm_gh0, tm_gmain, tm_h1, tm_h2);
+  } else {
+    if (relu) umma_block_bwd2_kernel<true, false><<<grid, B2_THREADS, bwd2_smem(), st>>>(a, tm_h0, tm_gout, tm_gh0, tm_gmain, tm_h1, tm_h2);
+    else umma_block_bwd2_kernel<false, false><<<grid, B2_THREADS, bwd2_smem(), st>>>(a, tm_h0, tm_gout, tm_gh0, tm_gmain, tm_h1, tm_h2);
+  }
   AERO_LAUNCH_CHECK();
   return AERO_OK;
 }

@@ -27,6 +27,7 @@ struct UmmaArgs {
   float* w_part;
   __nv_bfloat16* h0;   // fwd: optional output; bwd: optional input replacing the layer-0 recompute
   __nv_bfloat16* main_lat;   // fwd, main_f32: optional bf16 copy of the staged (scaled) main rows
+  __nv_bfloat16* hh[2];      // fwd: optional outputs H_1, H_2 (kept for a backward without recompute)
 };
 
 constexpr int UMMA_MAX_L = 2;
@@ -356,6 +357,8 @@ static inline UmmaArgs make_uargs(const aero_block_desc* d) {
   a.out = reinterpret_cast<__nv_bfloat16*>(d->out);
   a.h0 = reinterpret_cast<__nv_bfloat16*>(d->h0);
   a.main_lat = reinterpret_cast<__nv_bfloat16*>(d->main_lat);
+  a.hh[0] = reinterpret_cast<__nv_bfloat16*>(d->h_hidden[0]);
+  a.hh[1] = reinterpret_cast<__nv_bfloat16*>(d->h_hidden[1]);
   a.agg = d->agg; a.agg_part = nullptr;
   a.g_out = reinterpret_cast<const __nv_bfloat16*>(d->g_out);
   a.g_agg = d->g_agg; a.g_main = d->g_main;

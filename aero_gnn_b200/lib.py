@@ -32,7 +32,7 @@ class BlockDesc(C.Structure):
         ("out", C.c_void_p), ("agg", C.c_void_p),
         ("g_out", C.c_void_p), ("g_agg", C.c_void_p), ("g_main", C.c_void_p), ("g_h0", C.c_void_p),
         ("g_w", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("h0", C.c_void_p),
-        ("main_lat", C.c_void_p),
+        ("main_lat", C.c_void_p), ("h_hidden", C.c_void_p * 2),
     ]
 
 

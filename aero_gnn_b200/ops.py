@@ -174,6 +174,22 @@ def build_graph_plan(edge_index: torch.Tensor, num_nodes: int) -> GraphPlan:
     return GraphPlan(E, N, rowptr, perm, src, dst, sptr, sperm)
 
 
+def content_key(t: Optional[torch.Tensor]) -> tuple:
+    """Cache key of a device tensor's contents: the 64-bit kernel hash plus an independent 64-bit check word (a
+    position-weighted wrap-around sum computed by a different code path), so a hit on one mesh's entry by another
+    mesh would need both to collide."""
+    if t is None:
+        return (0, 0, 0)
+    tc = t.contiguous()
+    raw = tc.view(torch.uint8).view(-1)
+    if raw.numel() % 8:
+        raw = torch.cat([raw, raw.new_zeros(8 - raw.numel() % 8)])
+    words = raw.view(torch.int64)
+    weights = torch.arange(1, words.numel() + 1, device=words.device, dtype=torch.int64) * 0x1E3779B97F4A7C15
+    check = int((words * weights).sum().item())              # int64 wrap-around arithmetic
+    return (content_hash(words), check, int(words.numel()))
+
+
 def content_hash(t: torch.Tensor) -> int:
     _require_cuda(t)
     lib = _l.load()
@@ -208,7 +224,7 @@ class PlanCache:
             if ref() is edge_index and ver == edge_index._version and ptr == edge_index.data_ptr() and n == num_nodes:
                 return plan
         ei = edge_index.long().contiguous()
-        key = (content_hash(ei), int(ei.size(1)), int(num_nodes), str(ei.device))
+        key = (content_key(ei), int(ei.size(1)), int(num_nodes), str(ei.device))
         plan = self._by_hash.get(key)
         if plan is None:
             plan = build_graph_plan(ei, num_nodes)
@@ -310,6 +326,24 @@ def choose_path(dtype: torch.dtype, act: str, L: int = 0, backward: bool = False
     return _l.AERO_PATH_SIMT
 
 
+def keeps_hidden(keep_h0: bool, L_edge: int, L_node: int, rows_e: int, rows_n: int, K: int, device) -> bool:
+    """Keep-all policy (opt-in): with kept h_0 and L = 2 blocks the forward also keeps H_1 and H_2 of both blocks
+    (K steps x (E + N) x 512 B) and the backward kernels skip the recompute of the hidden layers.  Same bits either way.
+    Measured on C5 (B200): edge backward 3.78 -> 3.37 ms, node backward 0.75 -> 0.71 ms, but the forward's extra tile
+    stores cost as much (edge 2.18 -> 2.49 ms, node 0.41 -> 0.50 ms): 137.8 vs 137.4 ms per step for +52 GB of kept
+    rows -- a wash, so the default stays the lean policy (AERO_KEEP_ACTS=h0); =all selects this one, =auto selects it
+    when the extra rows take less than 40 % of the free device memory."""
+    if not keep_h0 or L_edge != 2 or L_node != 2 or os.environ.get("AERO_BWD_V1", "0") == "1":
+        return False
+    mode = os.environ.get("AERO_KEEP_ACTS", "h0")
+    if mode == "all":
+        return True
+    if mode != "auto":
+        return False
+    free, _total = torch.cuda.mem_get_info(device)
+    return K * (rows_e + rows_n) * 2 * D * 2 < 0.4 * free
+
+
 def keeps_h0(*paths: int) -> bool:
     """The first hidden activation is kept from the forward when every kernel of a stack runs on tcgen05
     (AERO_KEEP_H0=0 switches back to recomputing it, trading 256 B/row of memory for time)."""
@@ -370,7 +404,7 @@ def _desc(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, main
 def block_fwd(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, main_scale=None, rowptr=None,
               want_agg=False, kind=None, h0_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
               agg_out: Optional[torch.Tensor] = None, agg_clear: bool = True, rows: Optional[tuple] = None,
-              main_lat_out: Optional[torch.Tensor] = None):
+              main_lat_out: Optional[torch.Tensor] = None, hidden_out: Optional[tuple] = None):
     """Forward of one fused block; returns (out, agg or None).  `h0_out` ([rows,128], latent dtype, tcgen05 path
     only) receives the first hidden activation so that the backward does not have to recompute it.
 
@@ -398,6 +432,8 @@ def block_fwd(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, 
     d.h0 = h0_out.data_ptr() if h0_out is not None else None
     # tcgen05 path, fp32 `main` (node block): latent-dtype copy of the staged rows round(main * main_scale)
     d.main_lat = main_lat_out.data_ptr() if main_lat_out is not None else None
+    if hidden_out is not None:      # keep-all policy: H_1, H_2 stored for a backward without recompute (L == 2)
+        d.h_hidden[0], d.h_hidden[1] = hidden_out[0].data_ptr(), hidden_out[1].data_ptr()
     if not agg_clear:
         d.flags = _l.AERO_BLOCK_AGG_NO_CLEAR
     if rows is not None:
@@ -419,6 +455,9 @@ def block_fwd(prep: PreparedBlock, main, resid, P, idx0, idx1, poff0, poff1, *, 
             d.idx1 = idx1.data_ptr() + r0 * 4
         if h0_out is not None:
             d.h0 = h0_out.data_ptr() + r0 * D * h0_out.element_size()
+        if hidden_out is not None:
+            for i in range(2):
+                d.h_hidden[i] = hidden_out[i].data_ptr() + r0 * D * hidden_out[i].element_size()
     ws = _workspace(lib.aero_block_workspace_bytes(C.byref(d), 0), P.device)
     d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
     tok = PROFILE.begin(kind)
@@ -441,7 +480,7 @@ def block_bwd(prep: PreparedBlock, main, P, idx0, idx1, poff0, poff1, g_out, *, 
               has_resid_grad=False, g_main_out: Optional[torch.Tensor] = None, kind=None,
               h0: Optional[torch.Tensor] = None, n_nodes: Optional[int] = None,
               rowptr: Optional[torch.Tensor] = None, g_w_out: Optional[torch.Tensor] = None,
-              main_is_lat_copy: bool = False):
+              main_is_lat_copy: bool = False, hidden: Optional[tuple] = None):
     """Backward of one fused block; returns (g_main, g_h0, g_w_packed[fp32], W_main slot zero).  With `h0` (the
     rows kept by block_fwd(h0_out=...)) layer 0 is not recomputed and `P` may be None.  `rowptr` (receiver CSR of
     the rows, with `g_agg`) lets the TMA-fed kernel take d(beta)'s receiver part as sum_n deg(n) g_agg[n]."""
@@ -459,6 +498,8 @@ def block_bwd(prep: PreparedBlock, main, P, idx0, idx1, poff0, poff1, g_out, *, 
     d = _desc(prep, main, None, P, idx0, idx1, poff0, poff1, main_scale=main_scale, n_nodes=n_nodes, like=g_out,
               rowptr=rowptr)
     d.h0 = h0.data_ptr() if h0 is not None else None
+    if hidden is not None:          # H_1, H_2 kept by block_fwd(hidden_out=...): no recompute of the hidden layers
+        d.h_hidden[0], d.h_hidden[1] = hidden[0].data_ptr(), hidden[1].data_ptr()
     rows = main.size(0)
     g_main_dtype = main.dtype
     if main_is_lat_copy:

@@ -211,6 +211,7 @@ class PartitionedStackFn(torch.autograd.Function):
         paths_bwd = (ops.choose_path(dt, cfg.act_edge, cfg.L_edge, backward=True),
                      ops.choose_path(dt, cfg.act_node, cfg.L_node, backward=True))
         keep_h0 = ops.keeps_h0(path_e, path_n, *paths_bwd)
+        keep_all = ops.keeps_hidden(keep_h0, cfg.L_edge, cfg.L_node, plan.E, n_own, K, x.device)
         split = 0 < E_int < plan.E           # interior edges first, boundary edges after the halo arrived
         saved, preps = [], []
         x_ext = x.new_empty((plan.N, D))
@@ -229,36 +230,41 @@ class PartitionedStackFn(torch.autograd.Function):
             torch.addmm(bp, x_cur, wt, out=P[:n_own])
             h0e = torch.empty_like(e) if keep_h0 else None
             h0n = torch.empty_like(x) if keep_h0 else None
+            hhe = (torch.empty_like(e), torch.empty_like(e)) if keep_all else None
+            hhn = (torch.empty_like(x), torch.empty_like(x)) if keep_all else None
             e_new = torch.empty_like(e)
             agg_full = torch.empty((plan.N, D), dtype=torch.float32, device=dev)
             if split:
                 ops.block_fwd(pe, e, e, P, plan.src, plan.dst, 0, D, rowptr=plan.rowptr, kind="edge_fwd",
-                              h0_out=h0e, out=e_new, agg_out=agg_full, rows=(0, E_int))
+                              h0_out=h0e, out=e_new, agg_out=agg_full, rows=(0, E_int), hidden_out=hhe)
             ex.forward_finish(tok)
             if plan.N > n_own:
                 torch.addmm(bp, x_ext[n_own:], wt, out=P[n_own:])
             if split:
                 ops.block_fwd(pe, e, e, P, plan.src, plan.dst, 0, D, rowptr=part.rowptr_boundary, kind="edge_fwd_b",
-                              h0_out=h0e, out=e_new, agg_out=agg_full, agg_clear=False, rows=(E_int, plan.E))
+                              h0_out=h0e, out=e_new, agg_out=agg_full, agg_clear=False, rows=(E_int, plan.E),
+                              hidden_out=hhe)
             else:
                 ops.block_fwd(pe, e, e, P, plan.src, plan.dst, 0, D, rowptr=plan.rowptr, kind="edge_fwd",
-                              h0_out=h0e, out=e_new, agg_out=agg_full)
+                              h0_out=h0e, out=e_new, agg_out=agg_full, hidden_out=hhe)
             agg = agg_full[:n_own]
             # x' goes straight into the own rows of the next step's extended row matrix
             x_next = x.new_empty((plan.N, D)) if k + 1 < K else None
             out_rows = x_next[:n_own] if x_next is not None else None
             agg_lat = torch.empty_like(x) if (keep_h0 and dt != torch.float32) else None
             x_new, _ = ops.block_fwd(pn, agg, x_cur, P, None, None, 2 * D, 0, main_scale=scale, kind="node_fwd",
-                                     h0_out=h0n, out=out_rows, main_lat_out=agg_lat)
+                                     h0_out=h0n, out=out_rows, main_lat_out=agg_lat, hidden_out=hhn)
             # x_ext and (h_0 of both blocks | P) are kept so the backward needs no second halo exchange; with kept h_0
             # the aggregate is kept as the latent-dtype copy the node kernel made of its staged rows
             saved += [x_ext, e, agg_lat if agg_lat is not None else agg, h0e, h0n] if keep_h0 else [x_ext, e, agg, P, P]
+            if keep_all:
+                saved += [hhe[0], hhe[1], hhn[0], hhn[1]]
             e = e_new
             if x_next is not None:
                 x_ext = x_next
         ctx.cfg, ctx.part, ctx.K = cfg, part, K
         ctx.set_materialize_grads(False)
-        ctx.paths, ctx.keep_h0 = paths_bwd, keep_h0
+        ctx.paths, ctx.keep_h0, ctx.keep_all = paths_bwd, keep_h0, keep_all
         # the weight images of the forward serve the backward too when both run on the same kernel family
         ctx.preps = preps if (path_e, path_n) == paths_bwd else None
         ctx.save_for_backward(*saved, *flat)
@@ -270,7 +276,8 @@ class PartitionedStackFn(torch.autograd.Function):
         plan, ex, n_own = part.plan, part.exchanger, part.n_own
         path_e, path_n = ctx.paths
         saved = ctx.saved_tensors
-        acts, flat = saved[: 5 * K], saved[5 * K:]
+        S = 9 if ctx.keep_all else 5
+        acts, flat = saved[: S * K], saved[S * K:]
         dt = acts[0].dtype
         G_x = torch.zeros_like(acts[0][:n_own]) if G_x is None else G_x.contiguous().to(dt)
         G_e = torch.zeros_like(acts[1]) if G_e is None else G_e.contiguous().to(dt).clone()
@@ -279,7 +286,8 @@ class PartitionedStackFn(torch.autograd.Function):
         reduce = (lambda t: dist.all_reduce(t, group=part.group, async_op=True)) if part.world > 1 else None
         sink = GradSink(K, cfg.L_edge, cfg.L_node, acts[0].device, reduce=reduce)
         for k in reversed(range(K)):
-            x_ext, e, agg, a1, a2 = acts[5 * k: 5 * k + 5]
+            x_ext, e, agg, a1, a2 = acts[S * k: S * k + 5]
+            hhe, hhn = (acts[S * k + 5: S * k + 7], acts[S * k + 7: S * k + 9]) if ctx.keep_all else (None, None)
             P, h0e, h0n = (None, a1, a2) if ctx.keep_h0 else (a1, None, None)
             x = x_ext[:n_own]
             w_edge, w_node, w_proj, b_proj = flat[4 * k: 4 * k + 4]
@@ -290,7 +298,8 @@ class PartitionedStackFn(torch.autograd.Function):
                 pn = ops.PreparedBlock(w_node, cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
             lat = ctx.keep_h0 and agg.dtype != torch.float32
             g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale, kind="node_bwd",
-                                               h0=h0n, n_nodes=plan.N, g_w_out=sink.w_node(k), main_is_lat_copy=lat)
+                                               h0=h0n, n_nodes=plan.N, g_w_out=sink.w_node(k), main_is_lat_copy=lat,
+                                               hidden=hhn)
             if lat:
                 ops.wgrad_into(g_wn, g_h0n, agg)
             else:
@@ -298,7 +307,7 @@ class PartitionedStackFn(torch.autograd.Function):
                 ops.wgrad_into(g_wn, g_h0n, agg_eff.to(dt))
             G_e, g_h0e, g_we = ops.block_bwd(pe, e, P, plan.src, plan.dst, 0, D, G_e, g_agg=g_agg, has_resid_grad=True,
                                              g_main_out=G_e, kind="edge_bwd", h0=h0e, n_nodes=plan.N,
-                                             rowptr=plan.rowptr, g_w_out=sink.w_edge(k))
+                                             rowptr=plan.rowptr, g_w_out=sink.w_edge(k), hidden=hhe)
             ops.wgrad_into(g_we, g_h0e, e)
             g_psd = torch.empty((plan.N, 2 * D), dtype=dt, device=e.device)   # [g_P_s | g_P_d] over local rows
             ops.segment_reduce(g_h0e, plan.sptr, plan.sperm, plan.N, out=g_psd[:, :D])

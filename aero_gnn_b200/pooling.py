@@ -155,14 +155,61 @@ def _hash_any(t: Optional[torch.Tensor]) -> int:
     return ops.content_hash(b)
 
 
+def _ident(*tensors):
+    """Identity of live tensors at their current version (no device work): (weakrefs, fingerprint)."""
+    import weakref
+    refs, fp = [], []
+    for t in tensors:
+        if t is None:
+            refs.append(None)
+            fp.append(None)
+        else:
+            try:
+                refs.append(weakref.ref(t))
+            except TypeError:
+                return None, None
+            fp.append((t.data_ptr(), t._version, tuple(t.shape), t.dtype))
+    return refs, tuple(fp)
+
+
+def _same(last, tensors, extra) -> bool:
+    if last is None:
+        return False
+    refs, fp, ex, _ = last
+    if ex != extra:
+        return False
+    for r, t in zip(refs, tensors):
+        if (r is None) != (t is None) or (r is not None and r() is not t):
+            return False
+    return _ident(*tensors)[1] == fp
+
+
 class PoolCache:
+    """Pool levels keyed by content (kernel hash + independent check word, ops.content_key).  Fast path: the same
+    live tensor objects at the same version -> no device work and no host sync at all (a hierarchy is looked up on
+    every forward; three hashes with three read-backs per level would also make the forward uncapturable)."""
+
     def __init__(self, capacity: int = 64):
         self.capacity = capacity
         self._d: "OrderedDict[tuple, PoolLevel]" = OrderedDict()
+        self._last: dict = {}
 
     def get(self, edge_index, batch, pos, stride: int) -> PoolLevel:
-        key = (_hash_any(edge_index), _hash_any(batch), _hash_any(pos), int(stride), tuple(edge_index.shape),
-               int(batch.numel()), str(edge_index.device))
+        slot = (int(stride), int(batch.numel()), int(edge_index.shape[1]))
+        last = self._last.get(slot)
+        if _same(last, (edge_index, batch, pos), int(stride)):
+            return last[3]
+        key = (ops.content_key(edge_index), ops.content_key(batch), ops.content_key(pos), int(stride),
+               tuple(edge_index.shape), int(batch.numel()), str(edge_index.device))
+        lvl = self._get_slow(key, edge_index, batch, pos, stride)
+        refs, fp = _ident(edge_index, batch, pos)
+        if refs is not None:
+            if len(self._last) > 32:
+                self._last.clear()
+            self._last[slot] = (refs, fp, int(stride), lvl)
+        return lvl
+
+    def _get_slow(self, key, edge_index, batch, pos, stride: int) -> PoolLevel:
         lvl = self._d.get(key)
         if lvl is None:
             lvl = build_pool_level(edge_index, batch, pos, stride)
@@ -175,6 +222,7 @@ class PoolCache:
 
     def clear(self):
         self._d.clear()
+        self._last.clear()
 
 
 POOL_CACHE = PoolCache()

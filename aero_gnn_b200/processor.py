@@ -314,6 +314,7 @@ class MGNStackFn(torch.autograd.Function):
         paths_bwd = (ops.choose_path(x.dtype, cfg.act_edge, cfg.L_edge, backward=True),
                      ops.choose_path(x.dtype, cfg.act_node, cfg.L_node, backward=True))
         keep_h0 = ops.keeps_h0(path_e, path_n, *paths_bwd)
+        keep_all = ops.keeps_hidden(keep_h0, cfg.L_edge, cfg.L_node, plan.E, plan.N, K, x.device)
         saved, preps = [], []
         for k in range(K):
             w_edge, w_node, w_proj, b_proj = flat[4 * k: 4 * k + 4]
@@ -323,20 +324,24 @@ class MGNStackFn(torch.autograd.Function):
             P = torch.addmm(b_proj.detach(), x, w_proj.detach().t())
             h0e = torch.empty_like(e) if keep_h0 else None
             h0n = torch.empty_like(x) if keep_h0 else None
+            hhe = (torch.empty_like(e), torch.empty_like(e)) if keep_all else None     # H_1, H_2 of the edge block
+            hhn = (torch.empty_like(x), torch.empty_like(x)) if keep_all else None
             e_new, agg = ops.block_fwd(pe, e, e, P, plan.src, plan.dst, 0, D, rowptr=plan.rowptr, want_agg=True,
-                                       kind="edge_fwd", h0_out=h0e)
+                                       kind="edge_fwd", h0_out=h0e, hidden_out=hhe)
             # tcgen05 path: the node kernel also stores the rows its first GEMM consumed, round(agg * scale) in the
             # latent dtype -- what the backward's weight-gradient GEMM needs -- and the fp32 aggregate is not kept
             agg_lat = torch.empty_like(x) if (keep_h0 and x.dtype != torch.float32) else None
             x_new, _ = ops.block_fwd(pn, agg, x, P, None, None, 2 * D, 0, main_scale=scale, kind="node_fwd",
-                                     h0_out=h0n, main_lat_out=agg_lat)
+                                     h0_out=h0n, main_lat_out=agg_lat, hidden_out=hhn)
             # tcgen05 path: the first hidden activation of both blocks is kept (the backward then skips one gather,
             # one GEMM and one epilogue per tile and never reads P); CUDA-core path: P is kept and layer 0 recomputed
             saved += [x, e, agg_lat if agg_lat is not None else agg, h0e, h0n] if keep_h0 else [x, e, agg, P, P]
+            if keep_all:    # keep-all policy: the backward kernels read H_1, H_2 instead of recomputing them
+                saved += [hhe[0], hhe[1], hhn[0], hhn[1]]
             x, e = x_new, e_new
         ctx.cfg, ctx.plan, ctx.K = cfg, plan, K
         ctx.set_materialize_grads(False)
-        ctx.paths, ctx.keep_h0 = paths_bwd, keep_h0
+        ctx.paths, ctx.keep_h0, ctx.keep_all = paths_bwd, keep_h0, keep_all
         # the weight images of the forward serve the backward too when both run on the same kernel family
         ctx.preps = preps if (path_e, path_n) == paths_bwd else None
         ctx.save_for_backward(*saved, *flat)
@@ -347,7 +352,8 @@ class MGNStackFn(torch.autograd.Function):
         cfg, plan, K = ctx.cfg, ctx.plan, ctx.K
         path_e, path_n = ctx.paths
         saved = ctx.saved_tensors
-        acts, flat = saved[: 5 * K], saved[5 * K:]
+        S = 9 if ctx.keep_all else 5                 # saved tensors per step
+        acts, flat = saved[: S * K], saved[S * K:]
         dt = acts[0].dtype
         G_x = torch.zeros_like(acts[0]) if G_x is None else G_x.contiguous().to(dt)
         # G_e is updated in place layer by layer; the edge output is usually unused (no gradient materialised)
@@ -355,7 +361,8 @@ class MGNStackFn(torch.autograd.Function):
         scale = plan.inv_deg if cfg.mean else None
         sink = GradSink(K, cfg.L_edge, cfg.L_node, acts[0].device)
         for k in reversed(range(K)):
-            x, e, agg, a1, a2 = acts[5 * k: 5 * k + 5]
+            x, e, agg, a1, a2 = acts[S * k: S * k + 5]
+            hhe, hhn = (acts[S * k + 5: S * k + 7], acts[S * k + 7: S * k + 9]) if ctx.keep_all else (None, None)
             P, h0e, h0n = (None, a1, a2) if ctx.keep_h0 else (a1, None, None)
             w_edge, w_node, w_proj, b_proj = flat[4 * k: 4 * k + 4]
             if ctx.preps is not None:
@@ -367,7 +374,7 @@ class MGNStackFn(torch.autograd.Function):
             lat = ctx.keep_h0 and agg.dtype != torch.float32      # agg = latent-dtype copy of the scaled aggregate
             g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale,
                                                kind="node_bwd", h0=h0n, n_nodes=plan.N, g_w_out=sink.w_node(k),
-                                               main_is_lat_copy=lat)
+                                               main_is_lat_copy=lat, hidden=hhn)
             if lat:
                 ops.wgrad_into(g_wn, g_h0n, agg)
             else:
@@ -376,7 +383,7 @@ class MGNStackFn(torch.autograd.Function):
             # edge block: total gradient of e' = G_e + g_agg[receiver]
             G_e, g_h0e, g_we = ops.block_bwd(pe, e, P, plan.src, plan.dst, 0, D, G_e, g_agg=g_agg,
                                              has_resid_grad=True, g_main_out=G_e, kind="edge_bwd", h0=h0e,
-                                             n_nodes=plan.N, rowptr=plan.rowptr, g_w_out=sink.w_edge(k))
+                                             n_nodes=plan.N, rowptr=plan.rowptr, g_w_out=sink.w_edge(k), hidden=hhe)
             ops.wgrad_into(g_we, g_h0e, e)
             # gradients of the gathered projections: segmented sums by sender and by receiver
             # (both land in one [N, 2D] matrix, so the products with W_s | W_d are single K = 2D GEMMs)

@@ -200,6 +200,10 @@ typedef struct aero_block_desc {
    * i.e. round(main[r] * main_scale[r]) -- the node block's (scaled) aggregate in the latent dtype, which the caller's
    * weight-gradient GEMM  g_h0^T @ main  needs (saves a separate cast / scale pass over the fp32 aggregate). */
   void* main_lat;
+  /* optional [rows,128] rows of the hidden activations H_1, H_2 (latent dtype; AERO_PATH_UMMA, L == 2, together with
+   * h0).  fwd: stored when non-NULL.  bwd: read instead of recomputing the hidden layers (two GEMM phases and two
+   * epilogues per tile less; a memory-for-time policy: +256 B/row each, kept per step by the caller). */
+  void* h_hidden[2];
 } aero_block_desc;
 
 size_t aero_block_prepared_bytes(int L, int path);

@@ -26,7 +26,7 @@ def test_block_desc_matches_header_layout():
     import ctypes as C
     from aero_gnn_b200 import lib
     d = lib.BlockDesc
-    assert d.rows.offset == 32 and d.main.offset == 72 and C.sizeof(d) == 72 + 19 * 8 and d.h0.offset == 72 + 17 * 8
+    assert d.rows.offset == 32 and d.main.offset == 72 and C.sizeof(d) == 72 + 21 * 8 and d.h0.offset == 72 + 17 * 8
     assert d.main_lat.offset == 72 + 18 * 8 and d.flags.offset == 28
 
 

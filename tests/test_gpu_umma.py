@@ -272,3 +272,37 @@ def test_tma_backward_matches_first_generation_kernel(name, n, e):
     assert rel_l2(g2[0], g1[0]) < 5e-3 and rel_l2(g2[1], g1[1]) < 5e-3, (rel_l2(g2[0], g1[0]), rel_l2(g2[1], g1[1]))
     for k in g1[2]:
         assert rel_l2(g2[2][k], g1[2][k]) < 5e-3, (k, rel_l2(g2[2][k], g1[2][k]))
+
+
+@pytest.mark.parametrize("agg", ["add", "mean"])
+def test_keep_all_policy_equals_recompute_bit_for_bit(monkeypatch, agg):
+    """AERO_KEEP_ACTS=all (the forward also keeps H_1, H_2; the TMA-fed backward reads them instead of recomputing the
+    hidden layers) gives the same bits as AERO_KEEP_ACTS=h0: the kept tiles are exactly what the recompute produces."""
+    import aero_gnn_b200.models as M
+    from aero_gnn_b200 import ops
+    from aero_gnn_b200.meshes import wing_surface_mesh
+    from aero_gnn_b200.models._common import run_layers
+    dev = torch.device("cuda", 0)
+    mesh = wing_surface_mesh(61, 37)             # 2257 nodes, ragged last tiles
+    torch.manual_seed(4)
+    net = M.MeshGraphNet(6, 4, 5, processor_size=3, num_hidden_layers_node_processor=2,
+                         num_hidden_layers_edge_processor=2, aggregation=agg, do_concat_trick=True).to(dev).to(torch.bfloat16)
+    plan = ops.PLAN_CACHE.get(mesh.edge_index.to(dev), mesh.num_nodes)
+    g = torch.Generator().manual_seed(8)
+    x0 = torch.randn(mesh.num_nodes, 128, generator=g).to(dev, torch.bfloat16).requires_grad_(True)
+    e0 = torch.randn(mesh.num_edges, 128, generator=g).to(dev, torch.bfloat16).requires_grad_(True)
+    gx = torch.randn(mesh.num_nodes, 128, generator=g).to(dev, torch.bfloat16)
+    ge = torch.randn(mesh.num_edges, 128, generator=g).to(dev, torch.bfloat16)
+
+    def run(mode):
+        monkeypatch.setenv("AERO_KEEP_ACTS", mode)
+        for p in net.layers.parameters():
+            p.grad = None
+        x0.grad = e0.grad = None
+        x, e = run_layers(net.layers, plan, x0, e0)
+        torch.autograd.backward([x, e], [gx, ge])
+        return [x.detach().clone(), e.detach().clone(), x0.grad.clone(), e0.grad.clone()] + [p.grad.clone() for p in net.layers.parameters()]
+
+    a, b = run("all"), run("h0")
+    for i, (u, v) in enumerate(zip(a, b)):
+        assert torch.equal(u, v), i
