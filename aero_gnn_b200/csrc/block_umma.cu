@@ -113,6 +113,23 @@ umma_block_fwd_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_main, c
   const int act = RELU ? AERO_ACT_RELU : a.act;
 
   const int64_t tiles = (a.rows + 127) / 128;
+  // gather indices (and the two receiver ids across the tile edges) of a tile are fetched while the PREVIOUS tile of
+  // the group computes, so no tile starts by waiting for an index load
+  int nsrc = -1, ndst = -1, nprev = -2, nnext = -2;
+  auto fetch_indices = [&](int64_t t) {
+    nsrc = ndst = -1;
+    nprev = nnext = -2;
+    const int64_t r = t * 128 + gt;
+    if (t < tiles && gt < 128 && r < a.rows) {
+      nsrc = a.idx0 ? __ldg(a.idx0 + r) : (int)r;
+      ndst = a.idx1 ? __ldg(a.idx1 + r) : -1;
+      if (a.agg) {
+        if (lane == 0 && r > 0) nprev = __ldg(a.idx1 + r - 1);
+        if ((gt == 127 || r == a.rows - 1) && r + 1 < a.rows) nnext = __ldg(a.idx1 + r + 1);
+      }
+    }
+  };
+  fetch_indices((int64_t)blockIdx.x * FWD_GROUPS + grp);
   for (int64_t tile = (int64_t)blockIdx.x * FWD_GROUPS + grp; tile < tiles; tile += (int64_t)gridDim.x * FWD_GROUPS) {
     const int64_t row0 = tile * 128;
     const int nrows = (int)((a.rows - row0) < 128 ? (a.rows - row0) : 128);
@@ -139,8 +156,8 @@ umma_block_fwd_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_main, c
     if (gt < 128) {
       int64_t r = row0 + gt;
       bool ok = gt < nrows;
-      int i0 = ok ? (a.idx0 ? a.idx0[r] : (int)r) : 0;
-      int i1 = ok ? (a.idx1 ? a.idx1[r] : -1) : -1;
+      int i0 = ok ? nsrc : 0;
+      int i1 = ok ? ndst : -1;
       sidx0[gt] = i0;
       sidx1[gt] = i1;
       if (a.agg) {
@@ -148,8 +165,8 @@ umma_block_fwd_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_main, c
         // neighbours across the tile boundary are read straight from the (receiver-sorted) index list: no load
         // depends on another one
         int prev = __shfl_up_sync(0xffffffffu, i1, 1);
-        if (lane == 0) prev = (!ok || r == 0) ? -2 : a.idx1[r - 1];
-        const int next = (gt == nrows - 1 && r + 1 < a.rows) ? a.idx1[r + 1] : -2;
+        if (lane == 0) prev = (!ok || r == 0) ? -2 : nprev;
+        const int next = (gt == nrows - 1) ? nnext : -2;
         uint32_t m = __ballot_sync(0xffffffffu, ok && (gt == 0 || i1 != prev));
         if (lane == 0) gmask[gw] = m;
         if (gt == 0) gmask[4] = (prev == i1) ? 1u : 0u;              // head segment started in an earlier tile
@@ -192,16 +209,9 @@ umma_block_fwd_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_main, c
         prefetch_l2(p + 32);
       }
     }
-    // gather indices of the NEXT tile: their pre-projected rows are prefetched into L2 after this tile's first
-    // epilogue, so the layer-0 gathers of the next tile do not pay DRAM latency
-    int nsrc = -1, ndst = -1;
-    {
-      const int64_t r = (tile + (int64_t)gridDim.x * FWD_GROUPS) * 128 + gt;
-      if (gt < 128 && r < a.rows) {
-        nsrc = a.idx0 ? a.idx0[r] : (int)r;
-        ndst = a.idx1 ? a.idx1[r] : -1;
-      }
-    }
+    // gather indices of the NEXT tile (used at its start; their pre-projected rows are also prefetched into L2 after
+    // this tile's first epilogue, so the layer-0 gathers of the next tile do not pay DRAM latency)
+    fetch_indices(tile + (int64_t)gridDim.x * FWD_GROUPS);
 
     for (int layer = 0; layer <= L + 1; ++layer) {
       if (gw0) {   // first warp of the group, warp-uniform branch; one elected lane issues
