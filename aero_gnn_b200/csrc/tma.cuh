@@ -13,6 +13,12 @@ namespace tma {
 // host: tensor map of a row-major [rows,128] bf16 matrix, box = 64 columns (128 bytes) x 128 rows, SWIZZLE_128B.
 // Returns 0 on success; the driver entry point is resolved at run time (no link-time dependency on libcuda).
 int make_rows_map(const void* base, int64_t rows, CUtensorMap* out);
+// same for a matrix with `cols` (a multiple of 64) columns and a row stride of `ld` elements: panel p = columns [64p, 64p+64)
+int make_rows_map_ld(const void* base, int64_t rows, int64_t cols, int64_t ld, CUtensorMap* out);
+
+// host: 1-D tensor map over n int32 ids, box = `box` ids (box * 4 a multiple of 16 bytes), no swizzle; coordinates
+// outside [0, n) -- negative ones included -- are zero-filled
+int make_ids_map(const int32_t* base, int64_t n, uint32_t box, CUtensorMap* out);
 
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];\n" ::"l"(tm) : "memory");
@@ -23,6 +29,12 @@ __device__ __forceinline__ void load_panel(uint32_t dst_saddr, const CUtensorMap
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst_saddr),
       "l"(tm), "r"(panel * 64), "r"(row0), "r"(mbar_saddr)
       : "memory");
+}
+// ids [x0, x0 + box) of a make_ids_map tensor map -> dst (16-byte aligned)
+__device__ __forceinline__ void load_ids(uint32_t dst_saddr, const CUtensorMap* tm, int x0, uint32_t mbar_saddr) {
+  asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2}], [%3];\n" ::"r"(dst_saddr),
+               "l"(tm), "r"(x0), "r"(mbar_saddr)
+               : "memory");
 }
 // whole 128x128 row tile (two panels); the caller has armed the mbarrier with 32768 bytes
 __device__ __forceinline__ void load_tile(uint32_t dst_saddr, const CUtensorMap* tm, int row0, uint32_t mbar_saddr) {

@@ -181,7 +181,7 @@ def content_key(t: Optional[torch.Tensor]) -> tuple:
     if t is None:
         return (0, 0, 0)
     tc = t.contiguous()
-    raw = tc.view(torch.uint8).view(-1)
+    raw = tc.reshape(-1).view(torch.uint8)   # (an empty [2, 0] view may carry a non-unit last stride)
     if raw.numel() % 8:
         raw = torch.cat([raw, raw.new_zeros(8 - raw.numel() % 8)])
     words = raw.view(torch.int64)
@@ -474,6 +474,47 @@ def wgrad_into(g_w: torch.Tensor, g_h0: torch.Tensor, rows_in: torch.Tensor) -> 
     rows, written in fp32 straight into the packed gradient vector (no bf16 rounding of the result, no cast/copy
     launches)."""
     torch.mm(g_h0.t(), rows_in, out_dtype=torch.float32, out=g_w[: D * D].view(D, D))
+
+
+def own_wgrad(dtype: torch.dtype) -> bool:
+    """bf16 rows on a tcgen05 device go through aero_wgrad; AERO_WGRAD=lib keeps the library GEMMs (A/B measurements)."""
+    return dtype == torch.bfloat16 and bool(_l.load().aero_has_umma()) and os.environ.get("AERO_WGRAD", "own") != "lib"
+
+
+def wgrad(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, seg=None) -> None:
+    """out[128 a, 128] (fp32, contiguous) = A[rows, 128 a]^T @ B[rows, 128] on the warp-specialised tcgen05 / TMA kernel
+    (aero_wgrad); A may be a column block of a wider row matrix (unit column stride).  `seg = (dst, rowptr, n_nodes,
+    seg_out)`: also write the receiver sums of A's first 128 columns -- rows in receiver-CSR order -- into
+    seg_out [n_nodes, 128] (a column block of a wider matrix is fine).  bf16 rows only; fp32 rows use torch.mm."""
+    _require_cuda(A, B, out)
+    lib = _l.load()
+    rows = int(A.size(0))
+    a = A.size(1) // D
+    if A.dim() == 2 and (A.stride(1) != 1 or A.stride(0) % 8 or A.data_ptr() % 16):
+        A = A.contiguous()
+    if not B.is_contiguous() or B.data_ptr() % 16:
+        B = B.contiguous().clone() if B.data_ptr() % 16 else B.contiguous()
+    if (A.dtype != torch.bfloat16 or B.dtype != torch.bfloat16 or A.dim() != 2 or A.size(1) != a * D or a not in (1, 2)
+            or A.stride(1) != 1 or B.shape != (rows, D) or not B.is_contiguous() or out.dtype != torch.float32
+            or out.shape != (a * D, D) or not out.is_contiguous()):
+        raise RuntimeError("wgrad: A [rows, 128|256] and B [rows, 128] bf16 (unit column stride), out fp32 [128 a, 128]")
+    lda = A.stride(0) if rows > 1 else max(A.stride(0), A.size(1))
+    dst = rowptr = seg_out = None
+    n_nodes, seg_ld = 0, 0
+    if seg is not None:
+        dst, rowptr, n_nodes, seg_out = seg
+        if (seg_out.dim() != 2 or seg_out.size(1) != D or seg_out.stride(1) != 1 or seg_out.dtype != torch.bfloat16
+                or seg_out.size(0) < n_nodes or rowptr.numel() < n_nodes + 1 or dst.numel() != rows):
+            raise RuntimeError("wgrad: bad receiver-sum arguments")
+        seg_ld = seg_out.stride(0) if seg_out.size(0) > 1 else max(seg_out.stride(0), D)
+        if dst.data_ptr() % 16:      # the ids travel by TMA: 16-byte aligned base
+            dst = dst.clone()
+    ws = _workspace(lib.aero_wgrad_workspace_bytes(rows, a, int(seg is not None)), A.device)
+    with torch.cuda.device(A.device):
+        rc = lib.aero_wgrad(_ptr(A), lda, a, _ptr(B), rows, _ptr(out), _ptr(dst), _ptr(rowptr), int(n_nodes),
+                            _ptr(seg_out), seg_ld, _ptr(ws), ws.numel(), _stream())
+    _l.check(rc, "aero_wgrad")
+    LaunchCounter.add()
 
 
 def block_bwd(prep: PreparedBlock, main, P, idx0, idx1, poff0, poff1, g_out, *, g_agg=None, main_scale=None,

@@ -300,25 +300,33 @@ class PartitionedStackFn(torch.autograd.Function):
             g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale, kind="node_bwd",
                                                h0=h0n, n_nodes=plan.N, g_w_out=sink.w_node(k), main_is_lat_copy=lat,
                                                hidden=hhn)
-            if lat:
-                ops.wgrad_into(g_wn, g_h0n, agg)
+            own = ops.own_wgrad(dt)                  # warp-specialised tcgen05 / TMA row reductions (csrc/wgrad.cu)
+            agg_rows = agg if lat else (agg if scale is None else agg * scale[:, None]).to(dt)
+            if own:
+                ops.wgrad(g_h0n, agg_rows, g_wn[: D * D].view(D, D))
             else:
-                agg_eff = agg if scale is None else agg * scale[:, None]
-                ops.wgrad_into(g_wn, g_h0n, agg_eff.to(dt))
+                ops.wgrad_into(g_wn, g_h0n, agg_rows)
             G_e, g_h0e, g_we = ops.block_bwd(pe, e, P, plan.src, plan.dst, 0, D, G_e, g_agg=g_agg, has_resid_grad=True,
                                              g_main_out=G_e, kind="edge_bwd", h0=h0e, n_nodes=plan.N,
                                              rowptr=plan.rowptr, g_w_out=sink.w_edge(k), hidden=hhe)
-            ops.wgrad_into(g_we, g_h0e, e)
             g_psd = torch.empty((plan.N, 2 * D), dtype=dt, device=e.device)   # [g_P_s | g_P_d] over local rows
             ops.segment_reduce(g_h0e, plan.sptr, plan.sperm, plan.N, out=g_psd[:, :D])
-            ops.segment_reduce(g_h0e, plan.rowptr, None, plan.N, out=g_psd[:, D:])
+            if own:
+                ops.wgrad(g_h0e, e, g_we[: D * D].view(D, D), seg=(plan.dst, plan.rowptr, plan.N, g_psd[:, D:]))
+            else:
+                ops.wgrad_into(g_we, g_h0e, e)
+                ops.segment_reduce(g_h0e, plan.rowptr, None, plan.N, out=g_psd[:, D:])
             g_ext = g_psd @ w_proj[:2 * D]                          # [n_local, D]
             tok = ex.backward_start(g_ext[n_own:], g_ext)           # halo-row gradients travel under the GEMMs below
             g_x = G_x + g_ext[:n_own]
             g_x.addmm_(g_h0n, w_proj[2 * D:])
             g_wproj = sink.w_proj(k)
-            torch.mm(g_psd.t(), x_ext, out_dtype=torch.float32, out=g_wproj[:2 * D])
-            torch.mm(g_h0n.t(), x, out_dtype=torch.float32, out=g_wproj[2 * D:])
+            if own:
+                ops.wgrad(g_psd, x_ext, g_wproj[:2 * D])
+                ops.wgrad(g_h0n, x, g_wproj[2 * D:])
+            else:
+                torch.mm(g_psd.t(), x_ext, out_dtype=torch.float32, out=g_wproj[:2 * D])
+                torch.mm(g_h0n.t(), x, out_dtype=torch.float32, out=g_wproj[2 * D:])
             ex.backward_finish(tok, g_x)
             sink.step_done(k)
             G_x = g_x

@@ -375,26 +375,34 @@ class MGNStackFn(torch.autograd.Function):
             g_agg, g_h0n, g_wn = ops.block_bwd(pn, agg, P, None, None, 2 * D, 0, G_x, main_scale=scale,
                                                kind="node_bwd", h0=h0n, n_nodes=plan.N, g_w_out=sink.w_node(k),
                                                main_is_lat_copy=lat, hidden=hhn)
-            if lat:
-                ops.wgrad_into(g_wn, g_h0n, agg)
+            own = ops.own_wgrad(dt)                  # warp-specialised tcgen05 / TMA row reductions (csrc/wgrad.cu)
+            agg_rows = agg if lat else (agg if scale is None else agg * scale[:, None]).to(dt)
+            if own:
+                ops.wgrad(g_h0n, agg_rows, g_wn[: D * D].view(D, D))
             else:
-                agg_eff = agg if scale is None else agg * scale[:, None]
-                ops.wgrad_into(g_wn, g_h0n, agg_eff.to(dt))
+                ops.wgrad_into(g_wn, g_h0n, agg_rows)
             # edge block: total gradient of e' = G_e + g_agg[receiver]
             G_e, g_h0e, g_we = ops.block_bwd(pe, e, P, plan.src, plan.dst, 0, D, G_e, g_agg=g_agg,
                                              has_resid_grad=True, g_main_out=G_e, kind="edge_bwd", h0=h0e,
                                              n_nodes=plan.N, rowptr=plan.rowptr, g_w_out=sink.w_edge(k), hidden=hhe)
-            ops.wgrad_into(g_we, g_h0e, e)
             # gradients of the gathered projections: segmented sums by sender and by receiver
             # (both land in one [N, 2D] matrix, so the products with W_s | W_d are single K = 2D GEMMs)
             g_psd = torch.empty((plan.N, 2 * D), dtype=dt, device=x.device)
             ops.segment_reduce(g_h0e, plan.sptr, plan.sperm, plan.N, out=g_psd[:, :D])
-            ops.segment_reduce(g_h0e, plan.rowptr, None, plan.N, out=g_psd[:, D:])
+            if own:   # dW_e = g_h0e^T e and the receiver sums of g_h0e from one pass over the rows
+                ops.wgrad(g_h0e, e, g_we[: D * D].view(D, D), seg=(plan.dst, plan.rowptr, plan.N, g_psd[:, D:]))
+            else:
+                ops.wgrad_into(g_we, g_h0e, e)
+                ops.segment_reduce(g_h0e, plan.rowptr, None, plan.N, out=g_psd[:, D:])
             g_x = torch.addmm(G_x, g_psd, w_proj[:2 * D])
             g_x.addmm_(g_h0n, w_proj[2 * D:])
-            g_wproj = sink.w_proj(k)                 # fp32, written by the GEMMs
-            torch.mm(g_psd.t(), x, out_dtype=torch.float32, out=g_wproj[:2 * D])
-            torch.mm(g_h0n.t(), x, out_dtype=torch.float32, out=g_wproj[2 * D:])
+            g_wproj = sink.w_proj(k)                 # fp32, written by the reductions
+            if own:
+                ops.wgrad(g_psd, x, g_wproj[:2 * D])
+                ops.wgrad(g_h0n, x, g_wproj[2 * D:])
+            else:
+                torch.mm(g_psd.t(), x, out_dtype=torch.float32, out=g_wproj[:2 * D])
+                torch.mm(g_h0n.t(), x, out_dtype=torch.float32, out=g_wproj[2 * D:])
             sink.step_done(k)
             G_x = g_x
         grads: List[Optional[torch.Tensor]] = []
@@ -587,7 +595,8 @@ def _zero_idx(rows: int, device) -> torch.Tensor:
 class DenseTailFn(torch.autograd.Function):
     """out = LN(W_out act(.. act(W_1 act(z) + b_1) ..) + b_out) for z = the first Linear's output, bias included
     (reference models/mlp.py:40-51 after its first `layer(x)`).  The block kernel's first GEMM runs with
-    W_main = I and a zero pre-projection row, so h_0 = act(z); `w` is the packed vector of pack_block()."""
+    W_main = I and a zero pre-projection row, so h_0 = act(z); `w` is the packed vector of pack_block().  On the
+    tcgen05 path h_0 is kept, so the backward is the TMA-fed kernel (no recompute of layer 0)."""
 
     @staticmethod
     def forward(ctx, L: int, act: str, use_ln: bool, z: torch.Tensor, w: torch.Tensor):
@@ -595,19 +604,24 @@ class DenseTailFn(torch.autograd.Function):
         z = z.contiguous()
         P = torch.zeros((1, D), dtype=z.dtype, device=z.device)
         idx0 = _zero_idx(z.size(0), z.device)
-        prep = ops.PreparedBlock(w.detach(), L, ops.choose_path(z.dtype, act, L), act, use_ln)
-        out, _ = ops.block_fwd(prep, z, None, P, idx0, None, 0, 0, kind="dense_fwd")
-        ctx.meta = (L, act, use_ln, ops.choose_path(z.dtype, act, L, backward=True))
-        ctx.save_for_backward(z, w, P, idx0)
+        path = ops.choose_path(z.dtype, act, L)
+        path_b = ops.choose_path(z.dtype, act, L, backward=True)
+        prep = ops.PreparedBlock(w.detach(), L, path, act, use_ln)
+        h0 = torch.empty_like(z) if (ops.keeps_h0(path, path_b) and 1 <= L <= 2 and z.size(0) > 0) else None
+        out, _ = ops.block_fwd(prep, z, None, P, idx0, None, 0, 0, kind="dense_fwd", h0_out=h0)
+        ctx.meta = (L, act, use_ln, path_b)
+        ctx.has_h0 = h0 is not None
+        ctx.save_for_backward(z if h0 is None else h0, w, P, idx0)
         return out
 
     @staticmethod
     def backward(ctx, g):
         L, act, use_ln, path = ctx.meta
-        z, w, P, idx0 = ctx.saved_tensors
+        z, w, P, idx0 = ctx.saved_tensors          # z: the rows themselves, or the kept h_0 (z is then not needed)
         prep = ops.PreparedBlock(w, L, path, act, use_ln)
         # W_main = I: the gradient of the first pre-activation IS the gradient of z (g_main = g_h0 . I is ignored)
-        _, g_h0, g_w = ops.block_bwd(prep, z, P, idx0, None, 0, 0, g.contiguous().to(z.dtype), kind="dense_bwd")
+        _, g_h0, g_w = ops.block_bwd(prep, z, P, idx0, None, 0, 0, g.contiguous().to(z.dtype), kind="dense_bwd",
+                                     h0=z if ctx.has_h0 else None)
         return None, None, None, g_h0, g_w
 
 
@@ -623,7 +637,8 @@ def dense_tail(L: int, act: str, use_ln: bool, z: torch.Tensor, hidden: Sequence
 class DenseMLPFn(torch.autograd.Function):
     """A whole MLP whose input is D wide (the decoder, mgn.py:130): out = [LN](W_out act(.. act(W_0 x + b_0) ..) + b_out).
     W_0 is the block's real first GEMM, b_0 its single pre-projection row; a narrower last Linear is zero-padded to
-    D output columns by the caller (the padded columns are zeros and carry zero gradient)."""
+    D output columns by the caller (the padded columns are zeros and carry zero gradient).  h_0 is kept on the
+    tcgen05 path (TMA-fed backward)."""
 
     @staticmethod
     def forward(ctx, L: int, act: str, use_ln: bool, x: torch.Tensor, w: torch.Tensor, b0: torch.Tensor):
@@ -631,18 +646,22 @@ class DenseMLPFn(torch.autograd.Function):
         x = x.contiguous()
         P = b0.detach().to(x.dtype).reshape(1, D).contiguous()
         idx0 = _zero_idx(x.size(0), x.device)
-        prep = ops.PreparedBlock(w.detach(), L, ops.choose_path(x.dtype, act, L), act, use_ln)
-        out, _ = ops.block_fwd(prep, x, None, P, idx0, None, 0, 0, kind="dense_fwd")
-        ctx.meta = (L, act, use_ln, ops.choose_path(x.dtype, act, L, backward=True), b0.dtype)
-        ctx.save_for_backward(x, w, P, idx0)
+        path = ops.choose_path(x.dtype, act, L)
+        path_b = ops.choose_path(x.dtype, act, L, backward=True)
+        prep = ops.PreparedBlock(w.detach(), L, path, act, use_ln)
+        h0 = torch.empty_like(x) if (ops.keeps_h0(path, path_b) and 1 <= L <= 2 and x.size(0) > 0) else None
+        out, _ = ops.block_fwd(prep, x, None, P, idx0, None, 0, 0, kind="dense_fwd", h0_out=h0)
+        ctx.meta = (L, act, use_ln, path_b, b0.dtype)
+        ctx.save_for_backward(x, w, P, idx0, h0 if h0 is not None else x.new_empty(0))
         return out
 
     @staticmethod
     def backward(ctx, g):
         L, act, use_ln, path, b0_dtype = ctx.meta
-        x, w, P, idx0 = ctx.saved_tensors
+        x, w, P, idx0, h0 = ctx.saved_tensors
         prep = ops.PreparedBlock(w, L, path, act, use_ln)
-        g_x, g_h0, g_w = ops.block_bwd(prep, x, P, idx0, None, 0, 0, g.contiguous().to(x.dtype), kind="dense_bwd")
+        g_x, g_h0, g_w = ops.block_bwd(prep, x, P, idx0, None, 0, 0, g.contiguous().to(x.dtype), kind="dense_bwd",
+                                       h0=h0 if h0.numel() else None)
         ops.wgrad_into(g_w, g_h0, x)          # dW_0 = g_h0^T x (library GEMM, like the processor)
         return None, None, None, g_x, g_w, g_w[-D:].to(b0_dtype)   # last slot: column sums of g_h0 = d b_0
 

@@ -313,6 +313,21 @@ int aero_wec_fwd(const aero_wec_desc* d, void* stream);
 int aero_wec_bwd(const aero_wec_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Weight-gradient reduction over rows (tcgen05, warp-specialised, fed by TMA):
+ *     dW[128 a, 128] (fp32, contiguous) = A[rows, 128 a]^T  B[rows, 128]        a_panels = 1 or 2
+ *   A, B bf16 row matrices (row strides lda / 128 elements).  The first Linear's weight gradient of a block
+ *   (mgnLayer.py:97-103 backwards: g_h0^T e, g_h0n^T agg) and the projection weight gradients
+ *   [g_P_s | g_P_d]^T x, g_h0n^T x.  Optionally (seg_out != NULL; rows in receiver-CSR order, dst = receiver of each
+ *   row, rowptr = its CSR over n_nodes) the receiver sums of A's first 128 columns are taken from the same
+ *   shared-memory tiles: seg_out[n, 0:128] (bf16, row stride seg_ld) = sum of A rows [rowptr[n], rowptr[n+1]) --
+ *   the gradient of the receiver-side pre-projection P_d (mgnLayer.py:99), fp32 accumulation in CSR order.
+ * ------------------------------------------------------------------------------------------ */
+size_t aero_wgrad_workspace_bytes(int64_t rows, int a_panels, int with_seg);
+int aero_wgrad(const void* A, int64_t lda, int a_panels, const void* B, int64_t rows, float* dW,
+               const int32_t* dst, const int32_t* rowptr, int64_t n_nodes, void* seg_out, int64_t seg_ld,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Training-step tail (utils.py:191-195, train.py:207-211, :222).
  *
  * aero_mse_loss_grad: loss[0] = loss_scale * sum (pred - target)^2 and grad = grad_scale * (pred - target) in one pass
