@@ -54,6 +54,15 @@ __device__ __forceinline__ void store_tile(const CUtensorMap* tm, uint32_t src_s
                "r"(src_saddr + 16384u)
                : "memory");
 }
+// same into columns [col0, col0 + 128) of a wider matrix (a make_rows_map_ld map)
+__device__ __forceinline__ void store_tile_at(const CUtensorMap* tm, uint32_t src_saddr, int col0, int row0) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(tm), "r"(col0), "r"(row0),
+               "r"(src_saddr)
+               : "memory");
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(tm), "r"(col0 + 64),
+               "r"(row0), "r"(src_saddr + 16384u)
+               : "memory");
+}
 __device__ __forceinline__ void store_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 // the issuing thread's bulk stores have finished READING shared memory (the tiles may be overwritten)
 __device__ __forceinline__ void store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }

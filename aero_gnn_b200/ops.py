@@ -517,6 +517,52 @@ def wgrad(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, seg=None) -> N
     LaunchCounter.add()
 
 
+def row_gemm(blocks, W: torch.Tensor, *, w_mn: bool, nb: int = 1, bias: Optional[torch.Tensor] = None,
+             add: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[rows, 128 nb] = sum_ka blocks[ka] @ Wtile(ka) (+ bias) (+ add) on the warp-specialised tcgen05 / TMA kernel
+    (aero_row_gemm).  `blocks`: 1..3 bf16 [rows,128] matrices (column blocks of wider matrices are fine); W: bf16
+    [128 * len(blocks) * nb, 128] contiguous; w_mn=False: out = A W^T (nn.Linear layout, nb output blocks),
+    w_mn=True: out = [A_0 | A_1 | ..] W."""
+    _require_cuda(W, *blocks)
+    lib = _l.load()
+    na = len(blocks)
+    rows = int(blocks[0].size(0))
+    fixed = []
+    for b in blocks:
+        if b.dtype != torch.bfloat16 or b.dim() != 2 or b.size(0) != rows or b.size(1) != D:
+            raise RuntimeError("row_gemm: every K-block must be bf16 [rows, 128]")
+        if b.stride(1) != 1 or (rows > 1 and b.stride(0) % 8) or b.data_ptr() % 16:
+            b = b.contiguous()
+        fixed.append(b)
+    if W.dtype != torch.bfloat16 or W.shape != (D * na * nb, D) or not W.is_contiguous() or W.data_ptr() % 16:
+        raise RuntimeError("row_gemm: W must be a contiguous, 16-byte aligned bf16 [128 na nb, 128] matrix")
+    if out is None:
+        out = torch.empty((rows, D * nb), dtype=torch.bfloat16, device=W.device)
+    if (out.dtype != torch.bfloat16 or out.shape != (rows, D * nb) or out.stride(1) != 1 or out.data_ptr() % 16
+            or (rows > 1 and out.stride(0) % 8)):
+        raise RuntimeError("row_gemm: out must be bf16 [rows, 128 nb] with unit column stride")
+    if bias is not None and (bias.dtype != torch.bfloat16 or bias.numel() != D * nb or not bias.is_contiguous()):
+        raise RuntimeError("row_gemm: bias must be a contiguous bf16 [128 nb] vector")
+    if bias is not None and bias.data_ptr() % 16:
+        bias = bias.clone()
+    if add is not None:
+        if add.dtype != torch.bfloat16 or add.shape != (rows, D * nb):
+            raise RuntimeError("row_gemm: add must be bf16 [rows, 128 nb]")
+        if add.stride(1) != 1 or (rows > 1 and add.stride(0) % 8) or add.data_ptr() % 16:
+            add = add.contiguous()
+    if rows == 0:
+        return out
+    ld = lambda t: t.stride(0) if rows > 1 else max(t.stride(0), t.size(1))
+    ptrs = (C.c_void_p * 3)(*[b.data_ptr() for b in fixed], *([None] * (3 - na)))
+    lds = (C.c_int64 * 3)(*[ld(b) for b in fixed], *([0] * (3 - na)))
+    with torch.cuda.device(W.device):
+        rc = lib.aero_row_gemm(ptrs, lds, na, _ptr(W), int(bool(w_mn)), nb, _ptr(bias), _ptr(add),
+                               ld(add) if add is not None else 0, _ptr(out), ld(out), rows, _stream())
+    _l.check(rc, "aero_row_gemm")
+    LaunchCounter.add()
+    return out
+
+
 def block_bwd(prep: PreparedBlock, main, P, idx0, idx1, poff0, poff1, g_out, *, g_agg=None, main_scale=None,
               has_resid_grad=False, g_main_out: Optional[torch.Tensor] = None, kind=None,
               h0: Optional[torch.Tensor] = None, n_nodes: Optional[int] = None,

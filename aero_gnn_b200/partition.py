@@ -227,7 +227,11 @@ class PartitionedStackFn(torch.autograd.Function):
             tok = ex.forward_start(x_ext, out=x_ext[n_own:])
             P = x.new_empty((plan.N, w_proj.size(0)))
             wt, bp = w_proj.detach().t(), b_proj.detach()
-            torch.addmm(bp, x_cur, wt, out=P[:n_own])
+            own_rows = ops.own_wgrad(x.dtype)          # row GEMMs on csrc/rowgemm.cu instead of the library
+            if own_rows:
+                ops.row_gemm([x_cur], w_proj.detach(), w_mn=False, nb=3, bias=bp, out=P[:n_own])
+            else:
+                torch.addmm(bp, x_cur, wt, out=P[:n_own])
             h0e = torch.empty_like(e) if keep_h0 else None
             h0n = torch.empty_like(x) if keep_h0 else None
             hhe = (torch.empty_like(e), torch.empty_like(e)) if keep_all else None
@@ -239,7 +243,10 @@ class PartitionedStackFn(torch.autograd.Function):
                               h0_out=h0e, out=e_new, agg_out=agg_full, rows=(0, E_int), hidden_out=hhe)
             ex.forward_finish(tok)
             if plan.N > n_own:
-                torch.addmm(bp, x_ext[n_own:], wt, out=P[n_own:])
+                if own_rows:
+                    ops.row_gemm([x_ext[n_own:]], w_proj.detach(), w_mn=False, nb=3, bias=bp, out=P[n_own:])
+                else:
+                    torch.addmm(bp, x_ext[n_own:], wt, out=P[n_own:])
             if split:
                 ops.block_fwd(pe, e, e, P, plan.src, plan.dst, 0, D, rowptr=part.rowptr_boundary, kind="edge_fwd_b",
                               h0_out=h0e, out=e_new, agg_out=agg_full, agg_clear=False, rows=(E_int, plan.E),
@@ -316,10 +323,17 @@ class PartitionedStackFn(torch.autograd.Function):
             else:
                 ops.wgrad_into(g_we, g_h0e, e)
                 ops.segment_reduce(g_h0e, plan.rowptr, None, plan.N, out=g_psd[:, D:])
-            g_ext = g_psd @ w_proj[:2 * D]                          # [n_local, D]
-            tok = ex.backward_start(g_ext[n_own:], g_ext)           # halo-row gradients travel under the GEMMs below
-            g_x = G_x + g_ext[:n_own]
-            g_x.addmm_(g_h0n, w_proj[2 * D:])
+            if own:
+                # halo rows first (only the gathered projections reach them), so their gradients travel under the
+                # own rows' K = 384 contraction
+                g_halo = ops.row_gemm([g_psd[n_own:, :D], g_psd[n_own:, D:]], w_proj[:2 * D], w_mn=True)
+                tok = ex.backward_start(g_halo, g_halo)
+                g_x = ops.row_gemm([g_psd[:n_own, :D], g_psd[:n_own, D:], g_h0n], w_proj, w_mn=True, add=G_x)
+            else:
+                g_ext = g_psd @ w_proj[:2 * D]                          # [n_local, D]
+                tok = ex.backward_start(g_ext[n_own:], g_ext)           # halo-row gradients travel under the GEMMs below
+                g_x = G_x + g_ext[:n_own]
+                g_x.addmm_(g_h0n, w_proj[2 * D:])
             g_wproj = sink.w_proj(k)
             if own:
                 ops.wgrad(g_psd, x_ext, g_wproj[:2 * D])

@@ -321,7 +321,10 @@ class MGNStackFn(torch.autograd.Function):
             pe = ops.PreparedBlock(w_edge.detach(), cfg.L_edge, path_e, cfg.act_edge, cfg.use_ln)
             pn = ops.PreparedBlock(w_node.detach(), cfg.L_node, path_n, cfg.act_node, cfg.use_ln)
             preps.append((pe, pn))
-            P = torch.addmm(b_proj.detach(), x, w_proj.detach().t())
+            if ops.own_wgrad(x.dtype):   # P = x [W_s; W_d; W_nx]^T + b on the warp-specialised row-GEMM kernel
+                P = ops.row_gemm([x], w_proj.detach(), w_mn=False, nb=3, bias=b_proj.detach())
+            else:
+                P = torch.addmm(b_proj.detach(), x, w_proj.detach().t())
             h0e = torch.empty_like(e) if keep_h0 else None
             h0n = torch.empty_like(x) if keep_h0 else None
             hhe = (torch.empty_like(e), torch.empty_like(e)) if keep_all else None     # H_1, H_2 of the edge block
@@ -394,8 +397,11 @@ class MGNStackFn(torch.autograd.Function):
             else:
                 ops.wgrad_into(g_we, g_h0e, e)
                 ops.segment_reduce(g_h0e, plan.rowptr, None, plan.N, out=g_psd[:, D:])
-            g_x = torch.addmm(G_x, g_psd, w_proj[:2 * D])
-            g_x.addmm_(g_h0n, w_proj[2 * D:])
+            if own:   # g_x = [g_P_s | g_P_d | g_h0n] W + G_x: one K = 384 contraction, one rounding
+                g_x = ops.row_gemm([g_psd[:, :D], g_psd[:, D:], g_h0n], w_proj, w_mn=True, add=G_x)
+            else:
+                g_x = torch.addmm(G_x, g_psd, w_proj[:2 * D])
+                g_x.addmm_(g_h0n, w_proj[2 * D:])
             g_wproj = sink.w_proj(k)                 # fp32, written by the reductions
             if own:
                 ops.wgrad(g_psd, x, g_wproj[:2 * D])

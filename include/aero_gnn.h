@@ -328,6 +328,21 @@ int aero_wgrad(const void* A, int64_t lda, int a_panels, const void* B, int64_t 
                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Row GEMMs of a processor step outside the fused blocks (tcgen05, warp-specialised, fed by TMA; bf16 rows):
+ *     out[rows, 128 nb] = sum_{ka < na} A_ka[rows, 128] . Wtile(ka, nb_i)  (+ bias[128 nb])  (+ add[rows, 128 nb])
+ *   a_blocks[ka] / a_ld[ka]: the K-blocks, each a [rows,128] column block of a row matrix (row stride a_ld[ka]).
+ *   W: na * nb row tiles of 128 x 128 bf16, contiguous.  w_mn == 0: tile nb_i holds W[out, in] (K contiguous) --
+ *   out = A W^T, nn.Linear's layout: the sum-trick pre-projection  P = x [W_s; W_d; W_nx]^T + b  (na = 1, nb = 3;
+ *   mgnLayer.py:97-103 applied per node).  w_mn == 1: tile ka holds W[k, out] (outputs contiguous) -- out = A W:
+ *   the gradient of the node latents through that projection,  g_x = [g_P_s | g_P_d | g_h0n] W + G_x  (na = 3,
+ *   nb = 1), fp32 accumulation over K = 384 and one rounding.  Exactly one of na / nb may exceed 1 (na * nb <= 3).
+ *   out / add rows may be column blocks of wider matrices (row strides out_ld / add_ld, multiples of 8).
+ * ------------------------------------------------------------------------------------------ */
+int aero_row_gemm(const void* const* a_blocks, const int64_t* a_ld, int na, const void* W, int w_mn, int nb,
+                  const void* bias, const void* add, int64_t add_ld, void* out, int64_t out_ld, int64_t rows,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Training-step tail (utils.py:191-195, train.py:207-211, :222).
  *
  * aero_mse_loss_grad: loss[0] = loss_scale * sum (pred - target)^2 and grad = grad_scale * (pred - target) in one pass

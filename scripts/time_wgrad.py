@@ -45,3 +45,15 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
         ops.wgrad(G, X, out, seg=(plan.dst, plan.rowptr, N, psd[:, 128:]))
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=6, max_name_column_width=60))
+
+# row GEMMs of a step: projection P and back-projection g_x, against the library calls they replace
+Wp = (torch.randn(384, 128, device=dev) / 11).bfloat16()
+bp = torch.randn(384, device=dev).bfloat16()
+Gx = torch.randn(N, 128, device=dev).bfloat16()
+t = timeit(lambda: ops.row_gemm([Xn], Wp, w_mn=False, nb=3, bias=bp)); print(f"row_gemm P (N rows)        {t:.3f} ms  {N * 1024 / 1e6 / t:.0f} GB/s")
+t = timeit(lambda: torch.addmm(bp, Xn, Wp.t())); print(f"torch.addmm P              {t:.3f} ms")
+t = timeit(lambda: ops.row_gemm([psd[:, :128], psd[:, 128:], Gn], Wp, w_mn=True, add=Gx)); print(f"row_gemm g_x (K=384)       {t:.3f} ms  {N * 1280 / 1e6 / t:.0f} GB/s")
+def lib_gx():
+    g = torch.addmm(Gx, psd, Wp[:256])
+    g.addmm_(Gn, Wp[256:])
+t = timeit(lib_gx); print(f"torch addmm + addmm_ g_x   {t:.3f} ms")
