@@ -460,7 +460,9 @@ int umma_block_fwd(const aero_block_desc* d, cudaStream_t st) {
   UmmaArgs a = make_uargs(d);
   if (d->agg) {
     a.agg_part = reinterpret_cast<float*>(d->workspace);
-    if (!(d->flags & AERO_BLOCK_AGG_NO_CLEAR))
+    // no memset of the aggregate: every receiver with rows is written by its tile (or by the fix-up when its run
+    // straddles tiles), and the fix-up launch zeroes the receivers without rows
+    if (d->rows == 0 && !(d->flags & AERO_BLOCK_AGG_NO_CLEAR))
       AERO_CUDA(cudaMemsetAsync(d->agg, 0, (size_t)d->n_nodes * 128 * sizeof(float), st));
   }
   if (d->rows == 0) return AERO_OK;
@@ -504,7 +506,9 @@ int umma_block_fwd(const aero_block_desc* d, cudaStream_t st) {
   else
     umma_block_fwd_kernel<false><<<grid, FWD_THREADS, fwd_smem(d->L), st>>>(a, tm_main, tm_resid, tm_out, tm_h0, tm_mlat, tm_h1, tm_h2);
   AERO_LAUNCH_CHECK();
-  if (d->agg) return launch_agg_fixup(a.agg_part, d->rowptr, d->agg, d->rows, d->n_nodes, 128, d->idx1, st);
+  if (d->agg)
+    return launch_agg_fixup128(a.agg_part, d->rowptr, d->idx1, d->agg, d->rows, d->n_nodes,
+                               !(d->flags & AERO_BLOCK_AGG_NO_CLEAR), st);
   return AERO_OK;
 }
 

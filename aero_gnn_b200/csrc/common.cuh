@@ -174,6 +174,10 @@ int umma_prepare(const float* w, int L, void* prepared, cudaStream_t st);
 // agg partial fix-up shared by both paths: complete the receiver sums that straddle row tiles
 int launch_agg_fixup(const float* part, const int32_t* rowptr, float* agg, int64_t rows,
                      int64_t n_nodes, int tile_rows, const int32_t* dst, cudaStream_t st);
+// 128-row tiles (the tcgen05 forward): one warp per boundary; zero_empty also writes zeros into the rows of receivers
+// without any row, which replaces the memset of the whole aggregate
+int launch_agg_fixup128(const float* part, const int32_t* rowptr, const int32_t* dst, float* agg, int64_t rows,
+                        int64_t n_nodes, bool zero_empty, cudaStream_t st);
 // receiver sums taken tile by tile by aero_wgrad (bf16 rows, stride ld): complete the runs that straddle 128-row tiles
 // from the per-tile fp32 partial rows, and zero the rows of receivers without any row
 int launch_gpd_fixup(const float* part, const int32_t* rowptr, const int32_t* dst, __nv_bfloat16* out, int64_t ld,

@@ -124,6 +124,49 @@ __global__ void __launch_bounds__(256) segment_bcast_kernel(const T* __restrict_
 // One block per tile boundary; the block acts only if the run crossing the boundary starts in
 // the tile left of it (so each straddling node is handled exactly once).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fixup_store(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void fixup_store(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(p);
+  o[0] = __floats2bfloat162_rn(v.x, v.y);
+  o[1] = __floats2bfloat162_rn(v.z, v.w);
+}
+
+// One warp per item, lane = 4 columns.  Blocks [0, n_bound_blocks): item = tile boundary t0 | t0 + 1 -- the receiver
+// whose run of rows crosses it gets the sum of its per-tile partial rows, in tile order, from the warp of the tile the
+// run starts in.  Further blocks (launched only when the rows of receivers without any edge row must be defined): item
+// = 32 receivers; the ones with an empty run are written as zeros -- no tile ever wrote them, so no memset pass is needed.
+// Shared by the forward aggregate (fp32 rows) and the receiver sums aero_wgrad takes per tile (bf16 rows, stride ld).
+template <typename OutT>
+__global__ void __launch_bounds__(256) run_fixup_kernel(const float* __restrict__ part, const int32_t* __restrict__ rowptr,
+                                                        const int32_t* __restrict__ dst, OutT* __restrict__ out, int64_t ld,
+                                                        int64_t rows, int64_t n_nodes, int64_t n_bound_blocks) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if ((int64_t)blockIdx.x >= n_bound_blocks) {
+    const int64_t n0 = (w - n_bound_blocks * 8) * 32;
+    const int64_t n = n0 + lane;
+    uint32_t empty = __ballot_sync(0xffffffffu, n < n_nodes && rowptr[n + 1] == rowptr[n]);
+    for (; empty; empty &= empty - 1)
+      fixup_store(out + (size_t)(n0 + __ffs(empty) - 1) * ld + lane * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    return;
+  }
+  const int64_t t0 = w;
+  const int64_t last_row = (t0 + 1) * 128 - 1;
+  if (last_row + 1 >= rows) return;       // no boundary after the final tile
+  const int n = dst[last_row];
+  const int b = rowptr[n], e = rowptr[n + 1];
+  if (e <= last_row + 1) return;          // run ends at the boundary: complete
+  if (b / 128 != t0) return;              // run started in an earlier tile: another warp owns it
+  const int64_t t1 = ((int64_t)e - 1) / 128;
+  float4 acc = *reinterpret_cast<const float4*>(part + ((size_t)t0 * 2 + ((b % 128) == 0 ? 0 : 1)) * 128 + lane * 4);
+  for (int64_t t = t0 + 1; t <= t1; ++t) {
+    const float4 v = *reinterpret_cast<const float4*>(part + ((size_t)t * 2) * 128 + lane * 4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  fixup_store(out + (size_t)n * ld + lane * 4, acc);
+}
+
+// tile sizes other than 128 rows (the CUDA-core forward): one block per boundary, thread = column
 __global__ void __launch_bounds__(128) agg_fixup_kernel(const float* __restrict__ part, const int32_t* __restrict__ rowptr,
                                                         const int32_t* __restrict__ dst, float* __restrict__ agg,
                                                         int64_t rows, int tile_rows) {
@@ -139,43 +182,6 @@ __global__ void __launch_bounds__(128) agg_fixup_kernel(const float* __restrict_
   float acc = part[((size_t)t0 * 2 + ((b % tile_rows) == 0 ? 0 : 1)) * 128 + c];
   for (int64_t t = t0 + 1; t <= t1; ++t) acc += part[((size_t)t * 2) * 128 + c];
   agg[(size_t)n * 128 + c] = acc;
-}
-
-// Same for the receiver sums aero_wgrad takes per tile (bf16 output rows, stride ld).  Blocks [0, tiles-1): one per tile
-// boundary (see agg_fixup_kernel); blocks beyond: 128 receivers each (thread = receiver), rows of receivers without any
-// edge row are zeroed (no tile ever wrote them).
-__global__ void __launch_bounds__(256) gpd_fixup_kernel(const float* __restrict__ part, const int32_t* __restrict__ rowptr,
-                                                        const int32_t* __restrict__ dst, __nv_bfloat16* __restrict__ out,
-                                                        int64_t ld, int64_t rows, int64_t n_nodes, int64_t n_bound_blocks) {
-  // one warp per item, lane = 4 columns.  Blocks [0, n_bound_blocks): item = tile boundary t0 | t0 + 1 -- the receiver
-  // whose run of rows crosses it gets the sum of its per-tile partial rows, in tile order, from the block of the tile
-  // the run starts in.  Further blocks: item = 32 receivers; the ones without any row are written as zeros.
-  const int lane = threadIdx.x & 31;
-  const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if ((int64_t)blockIdx.x >= n_bound_blocks) {
-    const int64_t n0 = (w - n_bound_blocks * 8) * 32;
-    const int64_t n = n0 + lane;
-    uint32_t empty = __ballot_sync(0xffffffffu, n < n_nodes && rowptr[n + 1] == rowptr[n]);
-    for (; empty; empty &= empty - 1)
-      *reinterpret_cast<uint2*>(out + (size_t)(n0 + __ffs(empty) - 1) * ld + lane * 4) = make_uint2(0u, 0u);
-    return;
-  }
-  const int64_t t0 = w;
-  const int64_t last_row = (t0 + 1) * 128 - 1;
-  if (last_row + 1 >= rows) return;
-  const int n = dst[last_row];
-  const int b = rowptr[n], e = rowptr[n + 1];
-  if (e <= last_row + 1) return;          // run ends at the boundary: complete
-  if (b / 128 != t0) return;              // run started in an earlier tile: another warp owns it
-  const int64_t t1 = ((int64_t)e - 1) / 128;
-  float4 acc = *reinterpret_cast<const float4*>(part + ((size_t)t0 * 2 + ((b % 128) == 0 ? 0 : 1)) * 128 + lane * 4);
-  for (int64_t t = t0 + 1; t <= t1; ++t) {
-    const float4 v = *reinterpret_cast<const float4*>(part + ((size_t)t * 2) * 128 + lane * 4);
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-  }
-  __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(out + (size_t)n * ld + lane * 4);
-  o[0] = __floats2bfloat162_rn(acc.x, acc.y);
-  o[1] = __floats2bfloat162_rn(acc.z, acc.w);
 }
 
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int n_parts, size_t stride,
@@ -205,14 +211,25 @@ int launch_agg_fixup(const float* part, const int32_t* rowptr, float* agg, int64
   return AERO_OK;
 }
 
-int launch_gpd_fixup(const float* part, const int32_t* rowptr, const int32_t* dst, __nv_bfloat16* out, int64_t ld,
-                     int64_t rows, int64_t n_nodes, cudaStream_t st) {
+template <typename OutT>
+static int launch_run_fixup(const float* part, const int32_t* rowptr, const int32_t* dst, OutT* out, int64_t ld, int64_t rows,
+                            int64_t n_nodes, bool zero_empty, cudaStream_t st) {
   const int64_t tiles = cdiv(rows > 0 ? rows : 1, 128);
-  const int64_t n_bound = cdiv(tiles - 1, 8), n_zero = cdiv(n_nodes, 256);
+  const int64_t n_bound = cdiv(tiles - 1, 8), n_zero = zero_empty ? cdiv(n_nodes, 256) : 0;
   if (n_bound + n_zero <= 0) return AERO_OK;
-  gpd_fixup_kernel<<<(unsigned)(n_bound + n_zero), 256, 0, st>>>(part, rowptr, dst, out, ld, rows, n_nodes, n_bound);
+  run_fixup_kernel<OutT><<<(unsigned)(n_bound + n_zero), 256, 0, st>>>(part, rowptr, dst, out, ld, rows, n_nodes, n_bound);
   AERO_LAUNCH_CHECK();
   return AERO_OK;
+}
+
+int launch_agg_fixup128(const float* part, const int32_t* rowptr, const int32_t* dst, float* agg, int64_t rows,
+                        int64_t n_nodes, bool zero_empty, cudaStream_t st) {
+  return launch_run_fixup<float>(part, rowptr, dst, agg, 128, rows, n_nodes, zero_empty, st);
+}
+
+int launch_gpd_fixup(const float* part, const int32_t* rowptr, const int32_t* dst, __nv_bfloat16* out, int64_t ld,
+                     int64_t rows, int64_t n_nodes, cudaStream_t st) {
+  return launch_run_fixup<__nv_bfloat16>(part, rowptr, dst, out, ld, rows, n_nodes, true, st);
 }
 
 int launch_reduce_partials(const float* part, int n_parts, size_t stride, float* out, size_t n, cudaStream_t st) {
