@@ -108,7 +108,13 @@ class BiStridedMeshGraphNet(nn.Module):
             # node latents / positions: mean over the fine nodes of each coarse node
             x = SegmentReduceFn.apply(x, lvl.node_gptr, lvl.node_glist, lvl.f2c32, lvl.n_coarse, True)
             if p is not None:
-                p = ops.segment_reduce(p.contiguous(), lvl.node_gptr, lvl.node_glist, lvl.n_coarse, mean=True)
+                # coarse positions are a function of the level's key (connectivity, batch, positions): computed once
+                # per level, so the next level's lookup sees the same tensor object (identity fast path, no hashing)
+                cp = lvl.__dict__.get("_coarse_pos")
+                if cp is None:
+                    cp = ops.segment_reduce(p.contiguous(), lvl.node_gptr, lvl.node_glist, lvl.n_coarse, mean=True)
+                    lvl.__dict__["_coarse_pos"] = cp
+                p = cp
             # edge latents: mean over the fine edges of each coarse edge, straight into coarse CSR order
             e = _pool_edges(e, plan, lvl, cplan)
             ei, b, plan = lvl.coarse_edge_index, lvl.coarse_batch, cplan

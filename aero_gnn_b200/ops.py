@@ -207,7 +207,7 @@ def content_hash(t: torch.Tensor) -> int:
 class PlanCache:
     """Graph plans keyed by mesh connectivity.
 
-    Fast path: the same live tensor object at the same version -> no device work at all.
+    Fast path: a live tensor object seen before, at the same version -> no device work at all.
     Otherwise a 64-bit content hash of edge_index (one pass over 16E bytes + one 8-byte readback)
     finds the plan of a mesh seen before (DataLoader epochs revisit the same meshes).
     """
@@ -215,10 +215,10 @@ class PlanCache:
     def __init__(self, capacity: int = 64):
         self.capacity = capacity
         self._by_hash: "OrderedDict[tuple, GraphPlan]" = OrderedDict()
-        self._last = None  # (weakref, version, ptr, N, plan)
+        self._last: dict = {}  # id(edge_index) -> (weakref, version, ptr, N, plan): every level of a hierarchy has a slot
 
     def get(self, edge_index: torch.Tensor, num_nodes: int) -> GraphPlan:
-        last = self._last
+        last = self._last.get(id(edge_index))
         if last is not None:
             ref, ver, ptr, n, plan = last
             if ref() is edge_index and ver == edge_index._version and ptr == edge_index.data_ptr() and n == num_nodes:
@@ -234,14 +234,16 @@ class PlanCache:
         else:
             self._by_hash.move_to_end(key)
         try:
-            self._last = (weakref.ref(edge_index), edge_index._version, edge_index.data_ptr(), num_nodes, plan)
+            if len(self._last) >= 64:     # identities of dead tensors pile up over an epoch of fresh batches
+                self._last.clear()
+            self._last[id(edge_index)] = (weakref.ref(edge_index), edge_index._version, edge_index.data_ptr(), num_nodes, plan)
         except TypeError:
-            self._last = None
+            pass
         return plan
 
     def clear(self) -> None:
         self._by_hash.clear()
-        self._last = None
+        self._last.clear()
 
 
 PLAN_CACHE = PlanCache()
