@@ -16,11 +16,12 @@ lossf = torch.nn.MSELoss()
 def step():
     net.zero_grad(set_to_none=True)
     pred = net(na.to(torch.bfloat16), ea.to(torch.bfloat16), ei)
-    loss = lossf(pred.float(), tg)
+    from aero_gnn_b200.train_tail import mse_loss
+    loss = mse_loss(pred, tg)
     loss.backward()
     return float(loss.item())
 for _ in range(2): step()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
     step(); torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=60))
