@@ -668,7 +668,10 @@ class DenseMLPFn(torch.autograd.Function):
         prep = ops.PreparedBlock(w, L, path, act, use_ln)
         g_x, g_h0, g_w = ops.block_bwd(prep, x, P, idx0, None, 0, 0, g.contiguous().to(x.dtype), kind="dense_bwd",
                                        h0=h0 if h0.numel() else None)
-        ops.wgrad_into(g_w, g_h0, x)          # dW_0 = g_h0^T x (library GEMM, like the processor)
+        if ops.own_wgrad(x.dtype) and x.size(0) > 0:     # dW_0 = g_h0^T x, like the processor's first-layer gradients
+            ops.wgrad(g_h0, x, g_w[: D * D].view(D, D))
+        else:
+            ops.wgrad_into(g_w, g_h0, x)
         return None, None, None, g_x, g_w, g_w[-D:].to(b0_dtype)   # last slot: column sums of g_h0 = d b_0
 
 
