@@ -20,7 +20,7 @@ PROBE_LIB = PKG / "libaero_probe.so"     # hardware probes (include/aero_gnn_deb
 PROBE_SOURCES = ["umma_probe.cu"]
 
 SOURCES = ["abi.cu", "sort_plan.cu", "segment.cu", "block_simt.cu", "block_umma.cu", "block_umma_bwd.cu", "block_umma_bwd2.cu",
-           "bistride.cu", "train_tail.cu", "wgrad.cu", "rowgemm.cu", "tma.cu"]
+           "bistride.cu", "train_tail.cu", "wgrad.cu", "rowgemm.cu", "tma.cu", "thin_linear.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -110,6 +110,11 @@ SIGNATURES = {
                              C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "aero_row_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                 C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "aero_thin_linear_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                       C.c_void_p]),
+    "aero_thin_linear_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
+    "aero_thin_linear_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_size_t, C.c_void_p]),
     "aero_mse_workspace_bytes": (C.c_size_t, []),
     "aero_mse_loss_grad": (C.c_int, [C.c_void_p] * 4 + [C.c_int64] * 4 + [C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_size_t,
                                       C.c_void_p]),

@@ -3,7 +3,8 @@
 Parameter names are the checkpoint contract: `layers.{i}.weight|bias` and `layer_norm.weight|bias`
 (SURVEY.md section 8b).  Inside a processor step the Linear/LayerNorm chain is executed by the fused
 block kernels (processor.py reads the parameters through `split_first` / `tail`); called on its own
-(encoders) everything after its first Linear runs on the same fused block kernel (processor.DenseTailFn); a
+(encoders) its thin first Linear (K <= 16 raw features) is a streaming kernel (ops.ThinLinearFn) and everything
+after it runs on the same fused block kernel (processor.DenseTailFn); a
 128-wide input (the decoder) runs whole on it, a narrower last Linear zero-padded (processor.DenseMLPFn); shapes
 the kernel does not cover stay a dense row-wise chain of library ops on the GPU.  CPU tensors are refused.
 """
@@ -60,7 +61,12 @@ class MLP(nn.Module):
                 out = dense_mlp(len(hidden), self.activation_name, self.use_layer_norm, x, self.layers[0].weight,
                                 self.layers[0].bias, hidden, w_out, b_out, gamma, beta)
                 return out if w_out.size(0) == D else out[:, : w_out.size(0)]
-            z = self.layers[0](x)                      # [rows, in] x [in, 128]: a thin library GEMM, bias included
+            from .. import ops as _ops
+            lin0 = self.layers[0]
+            if _ops.thin_linear_ok(x, lin0):           # K <= 16 raw features: streaming kernel, d(W) + d(b) in one pass
+                z = _ops.ThinLinearFn.apply(x, lin0.weight, lin0.bias)
+            else:
+                z = lin0(x)                            # [rows, in] x [in, 128]: a library GEMM, bias included
             return dense_tail(len(hidden), self.activation_name, self.use_layer_norm, z, hidden, w_out, b_out,
                               gamma, beta)
         # shapes / activations the fused kernel does not cover: a dense row-wise chain of library ops on the GPU,

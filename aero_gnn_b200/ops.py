@@ -565,6 +565,51 @@ def row_gemm(blocks, W: torch.Tensor, *, w_mn: bool, nb: int = 1, bias: Optional
     return out
 
 
+class ThinLinearFn(torch.autograd.Function):
+    """z = x W^T + b for K = in_features <= 16 and 128 outputs (the encoders' first Linear, mgn.py:123-124) on
+    aero_thin_linear_{fwd,bwd}: d(W) and d(b) come from one pass over the gradient rows."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        _require_cuda(x, W, b)
+        lib = _l.load()
+        x = x if x.stride(1) == 1 else x.contiguous()
+        rows, K = int(x.size(0)), int(x.size(1))
+        Wc = W.detach().to(x.dtype).contiguous()
+        bc = b.detach().to(x.dtype).contiguous() if b is not None else None
+        out = torch.empty((rows, D), dtype=x.dtype, device=x.device)
+        ldx = x.stride(0) if rows > 1 else max(x.stride(0), K)
+        with torch.cuda.device(x.device):
+            rc = lib.aero_thin_linear_fwd(_ptr(x), ldx, _ptr(Wc), _ptr(bc), _ptr(out), rows, K, dtype_code(x), _stream())
+        _l.check(rc, "aero_thin_linear_fwd")
+        LaunchCounter.add()
+        ctx.save_for_backward(x, Wc)
+        ctx.meta = (W.dtype, b.dtype if b is not None else None, ldx)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, Wc = ctx.saved_tensors
+        w_dtype, b_dtype, ldx = ctx.meta
+        lib = _l.load()
+        rows, K = int(x.size(0)), int(x.size(1))
+        g = g.contiguous().to(x.dtype)
+        dwb = torch.empty((D, K + 1), dtype=torch.float32, device=x.device)
+        ws = _workspace(lib.aero_thin_linear_workspace_bytes(rows, K), x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.aero_thin_linear_bwd(_ptr(g), _ptr(x), ldx, _ptr(dwb), rows, K, dtype_code(x), _ptr(ws), ws.numel(),
+                                          _stream())
+        _l.check(rc, "aero_thin_linear_bwd")
+        LaunchCounter.add()
+        g_x = g @ Wc if ctx.needs_input_grad[0] else None      # raw features never need it
+        return g_x, dwb[:, :K].to(w_dtype), (dwb[:, K].to(b_dtype) if b_dtype is not None else None)
+
+
+def thin_linear_ok(x: torch.Tensor, lin) -> bool:
+    return (x.is_cuda and x.dim() == 2 and x.dtype in (torch.float32, torch.bfloat16) and lin.out_features == D
+            and 1 <= lin.in_features <= 16 and lin.weight.dtype == x.dtype)
+
+
 def block_bwd(prep: PreparedBlock, main, P, idx0, idx1, poff0, poff1, g_out, *, g_agg=None, main_scale=None,
               has_resid_grad=False, g_main_out: Optional[torch.Tensor] = None, kind=None,
               h0: Optional[torch.Tensor] = None, n_nodes: Optional[int] = None,

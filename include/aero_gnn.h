@@ -343,6 +343,18 @@ int aero_row_gemm(const void* const* a_blocks, const int64_t* a_ld, int na, cons
                   void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * The encoders' first Linear on raw features (mgn.py:123-124; mlp.py:40-44): K = in_features <= 16, 128 outputs.
+ *   fwd: out[rows,128] = x[rows,K] W^T + b      (x row stride ldx; W [128,K], b [128] or NULL; all of `dtype`)
+ *   bwd: dwb[128][K+1] (fp32) <- d(W)[c][k] = sum_r g[r][c] x[r][k]  and, in slot k = K, d(b)[c] = sum_r g[r][c]
+ *        from ONE pass over the gradient rows g[rows,128]; deterministic.
+ * ------------------------------------------------------------------------------------------ */
+int aero_thin_linear_fwd(const void* x, int64_t ldx, const void* W, const void* b, void* out, int64_t rows, int K,
+                         int dtype, void* stream);
+size_t aero_thin_linear_workspace_bytes(int64_t rows, int K);
+int aero_thin_linear_bwd(const void* g, const void* x, int64_t ldx, float* dwb, int64_t rows, int K, int dtype,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Training-step tail (utils.py:191-195, train.py:207-211, :222).
  *
  * aero_mse_loss_grad: loss[0] = loss_scale * sum (pred - target)^2 and grad = grad_scale * (pred - target) in one pass
