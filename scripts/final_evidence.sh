@@ -1,0 +1,24 @@
+#!/bin/bash
+# One gpurun call that refreshes the round's evidence (1 GPU):  bash scripts/final_evidence.sh
+# bench lines -> gpurun_out/r02_bench_*.json, ncu launch list -> r02_launches.csv, ncu --set full reports of the fused
+# block kernels / the row-GEMM and weight-gradient kernels -> r02_fwd.ncu-rep, r02_bwd.ncu-rep.  Every ncu pass runs
+# only after the same command has exited 0 without ncu.
+set -u
+O=gpurun_out
+mkdir -p $O
+timeout 300 python bench.py --steps 20 --warmup 5 > $O/r02_bench_c5.json 2> $O/r02_bench_c5.err || echo "c5 bench failed"
+timeout 120 python bench.py --config c2 --steps 20 --warmup 5 > $O/r02_bench_c2.json 2> $O/r02_bench_c2.err || echo "c2 bench failed"
+timeout 120 python bench.py --config c3 --steps 20 --warmup 5 > $O/r02_bench_c3.json 2> $O/r02_bench_c3.err || echo "c3 bench failed"
+CMD="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --graph off"
+if timeout 200 $CMD > $O/plain.json 2> $O/plain.err; then
+  timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/r02_launches.csv $CMD > $O/ncu_list.log 2>&1
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:'umma_block_fwd_kernel|row_gemm_kernel' --launch-count 3 \
+      -o $O/r02_fwd -f $CMD > $O/ncu_fwd.log 2>&1
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:'umma_block_bwd2_kernel|wgrad_kernel|row_gemm_kernel' \
+      --launch-skip 15 --launch-count 5 -o $O/r02_bwd -f $CMD > $O/ncu_bwd.log 2>&1
+else
+  echo "plain command failed; no ncu pass"
+fi
+python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1 && echo "smoke ok" || echo "smoke FAILED"
+tail -3 $O/smoke.log
+ls -la $O | grep r02_
