@@ -88,7 +88,7 @@ __device__ __forceinline__ void mask_epilogue_chunk(uint32_t taddr, uint8_t* Ht,
 // KEPT: the forward also kept H_1 .. H_L (aero_block_desc.h_hidden, L == 2): they are fetched by the TMA engine like
 // h_0 and the recompute of the hidden layers disappears -- two GEMM phases and two epilogues per tile less, for
 // +256 B/row/layer kept from the forward and read here.
-template <bool RELU, bool KEPT>
+template <bool RELU, bool KEPT, bool F32T>   // F32T: fp32 g_main rows leave through TMA (node block, !KEPT)
 __global__ void __launch_bounds__(B2_THREADS, 1)
 umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, const __grid_constant__ CUtensorMap tm_gout,
                        const __grid_constant__ CUtensorMap tm_gh0, const __grid_constant__ CUtensorMap tm_gmain,
@@ -172,7 +172,7 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
         tma::prefetch_map(&tm_h0);
         tma::prefetch_map(&tm_gout);
         tma::prefetch_map(&tm_gh0);
-        if (out_tma) tma::prefetch_map(&tm_gmain);
+        if (out_tma || F32T) tma::prefetch_map(&tm_gmain);
         const int r0 = (int)((int64_t)blockIdx.x * 128);
         mbar_expect_tx(bar_h0, TILE_BYTES);
         tma::load_tile(x_s + (uint32_t)pH0 * TILE_BYTES, &tm_h0, r0, bar_h0);
@@ -500,7 +500,8 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
       fence_after_sync();
       if (w0 && has_next) {
         if (KEPT) prefetch(L + 1);   // slot 1 held W_1 (consumed by phase 1): the next tile's W_out
-        else prefetch(2);            // slot 0 held W_main, just consumed: the next tile's second matrix
+        else if (!F32T) prefetch(2);     // slot 0 held W_main, just consumed: the next tile's second matrix
+        // (fp32 g_main: slot 0 first stages two of the four fp32 output panels; W_2 follows at the next tile's first GEMM)
       }
       uint8_t* O = X + (size_t)pG * TILE_BYTES;
       if (resid) {
@@ -525,7 +526,29 @@ umma_block_bwd2_kernel(UmmaArgs a, const __grid_constant__ CUtensorMap tm_h0, co
           }
         }
       }
-      if (a.main_f32) {
+      if (F32T) {
+        // fp32 rows (the node block's g_agg) leave through TMA as well: 128 x 128 fp32 = four 32-column panels; chunks
+        // 0, 1 stage theirs in the O tile, chunks 2, 3 in weight slot 0 (W_main, consumed by the GEMM above).  Row-per-
+        // lane 16-byte global stores would be 32 half-filled sectors per warp instruction (4096 requests per tile).
+        uint8_t* S = (ch < 2 ? O : Wslot) + (size_t)(ch & 1) * PANEL_BYTES;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(S + row * 128 + ((j ^ (row & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        wst &= ~7u;                  // slot 0 no longer holds W_main
+        fence_async_smem();
+        __syncthreads();
+        if (w0) {
+          if (elect_one()) {
+            const uint32_t o_s = x_s + (uint32_t)pG * TILE_BYTES;
+            tma::store_panel_f32(&tm_gmain, o_s, 0, (int)row0);
+            tma::store_panel_f32(&tm_gmain, o_s + PANEL_BYTES, 32, (int)row0);
+            tma::store_panel_f32(&tm_gmain, w_s, 64, (int)row0);
+            tma::store_panel_f32(&tm_gmain, w_s + PANEL_BYTES, 96, (int)row0);
+            tma::store_commit();   // the next tile's first GEMM waits for these reads before either region is reused
+          }
+          __syncwarp();
+        }
+      } else if (a.main_f32) {
         if (valid) {
           float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.g_main) + (row0 + row) * 128 + ch * 32);
 #pragma unroll
@@ -648,7 +671,7 @@ static size_t bwd2_smem() {
 bool umma_bwd2_applicable(const aero_block_desc* d) {
   if (d->h0 == nullptr || d->L < 1 || d->L > 2 || d->rows <= 0) return false;
   if (d->g_agg && !d->rowptr) return false;   // d(beta) needs the receiver degrees
-  const uintptr_t al = (uintptr_t)d->h0 | (uintptr_t)d->g_out | (uintptr_t)d->g_h0 | (d->main_f32 ? 0 : (uintptr_t)d->g_main);
+  const uintptr_t al = (uintptr_t)d->h0 | (uintptr_t)d->g_out | (uintptr_t)d->g_h0 | (uintptr_t)d->g_main;
   return (al & 15) == 0;
 }
 
@@ -659,7 +682,7 @@ int umma_block_bwd2(const aero_block_desc* d, UmmaArgs a, int grid, cudaStream_t
       tma::make_rows_map(kept ? d->h_hidden[1] : d->h0, d->rows, &tm_h2) ||
       tma::make_rows_map(d->h0, d->rows, &tm_h0) || tma::make_rows_map(d->g_out, d->rows, &tm_gout) ||
       tma::make_rows_map(d->g_h0, d->rows, &tm_gh0) ||
-      tma::make_rows_map(d->main_f32 ? d->g_out : d->g_main, d->rows, &tm_gmain)) {
+      (d->main_f32 ? tma::make_rows_map_f32(d->g_main, d->rows, &tm_gmain) : tma::make_rows_map(d->g_main, d->rows, &tm_gmain))) {
     set_error("umma_block_bwd2: cuTensorMapEncodeTiled failed");
     return AERO_ECUDA;
   }
@@ -667,20 +690,29 @@ int umma_block_bwd2(const aero_block_desc* d, UmmaArgs a, int grid, cudaStream_t
   int dev = 0;
   AERO_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    AERO_CUDA(cudaFuncSetAttribute(umma_block_bwd2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd2_smem()));
-    AERO_CUDA(cudaFuncSetAttribute(umma_block_bwd2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd2_smem()));
-    AERO_CUDA(cudaFuncSetAttribute(umma_block_bwd2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd2_smem()));
-    AERO_CUDA(cudaFuncSetAttribute(umma_block_bwd2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd2_smem()));
+#define AERO_B2_ATTR(R, K, F) \
+  AERO_CUDA(cudaFuncSetAttribute(umma_block_bwd2_kernel<R, K, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd2_smem()))
+    AERO_B2_ATTR(true, false, false); AERO_B2_ATTR(false, false, false);
+    AERO_B2_ATTR(true, true, false);  AERO_B2_ATTR(false, true, false);
+    AERO_B2_ATTR(true, false, true);  AERO_B2_ATTR(false, false, true);
+#undef AERO_B2_ATTR
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const bool relu = d->act == AERO_ACT_RELU;
+  const bool f32t = d->main_f32 && !kept;
+#define AERO_B2_LAUNCH(R, K, F) \
+  umma_block_bwd2_kernel<R, K, F><<<grid, B2_THREADS, bwd2_smem(), st>>>(a, tm_h0, tm_gout, tm_gh0, tm_gmain, tm_h1, tm_h2)
   if (kept) {
-    if (relu) umma_block_bwd2_kernel<true, true><<<grid, B2_THREADS, bwd2_smem(), st>>>(a, tm_h0, tm_gout, tm_gh0, tm_gmain, tm_h1, tm_h2);
-    else umma_block_bwd2_kernel<false, true><<<grid, B2_THREADS, bwd2_smem(), st>>>(a, tm_h0, tm_gout, tm_gh0, tm_gmain, tm_h1, tm_h2);
+    if (relu) AERO_B2_LAUNCH(true, true, false);
+    else AERO_B2_LAUNCH(false, true, false);
+  } else if (f32t) {
+    if (relu) AERO_B2_LAUNCH(true, false, true);
+    else AERO_B2_LAUNCH(false, false, true);
   } else {
-    if (relu) umma_block_bwd2_kernel<true, false><<<grid, B2_THREADS, bwd2_smem(), st>>>(a, tm_h0, tm_gout, tm_gh0, tm_gmain, tm_h1, tm_h2);
-    else umma_block_bwd2_kernel<false, false><<<grid, B2_THREADS, bwd2_smem(), st>>>(a, tm_h0, tm_gout, tm_gh0, tm_gmain, tm_h1, tm_h2);
+    if (relu) AERO_B2_LAUNCH(true, false, false);
+    else AERO_B2_LAUNCH(false, false, false);
   }
+#undef AERO_B2_LAUNCH
   AERO_LAUNCH_CHECK();
   return AERO_OK;
 }

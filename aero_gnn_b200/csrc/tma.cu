@@ -36,6 +36,18 @@ int make_rows_map_ld(const void* base, int64_t rows, int64_t cols, int64_t ld, C
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 1;
 }
+int make_rows_map_f32(const void* base, int64_t rows, CUtensorMap* out) {
+  EncodeTiledFn fn = resolve_encode();
+  if (!fn || rows <= 0 || ((uintptr_t)base & 15)) return 1;
+  const cuuint64_t dims[2] = {128, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {512};                         // bytes between rows
+  const cuuint32_t box[2] = {32, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1;
+}
 int make_ids_map(const int32_t* base, int64_t n, uint32_t box, CUtensorMap* out) {
   EncodeTiledFn fn = resolve_encode();
   if (!fn || n <= 0 || box == 0 || box > 256 || (box % 4) || ((uintptr_t)base & 15)) return 1;

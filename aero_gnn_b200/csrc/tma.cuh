@@ -16,6 +16,9 @@ int make_rows_map(const void* base, int64_t rows, CUtensorMap* out);
 // same for a matrix with `cols` (a multiple of 64) columns and a row stride of `ld` elements: panel p = columns [64p, 64p+64)
 int make_rows_map_ld(const void* base, int64_t rows, int64_t cols, int64_t ld, CUtensorMap* out);
 
+// host: tensor map of a row-major [rows,128] FP32 matrix, box = 32 columns (128 bytes) x 128 rows, SWIZZLE_128B: an fp32
+// row tile is four 16 KB panels with the same chunk swizzle as a bf16 panel (16-byte chunk c of row r at c ^ (r & 7))
+int make_rows_map_f32(const void* base, int64_t rows, CUtensorMap* out);
 // host: 1-D tensor map over n int32 ids, box = `box` ids (box * 4 a multiple of 16 bytes), no swizzle; coordinates
 // outside [0, n) -- negative ones included -- are zero-filled
 int make_ids_map(const int32_t* base, int64_t n, uint32_t box, CUtensorMap* out);
@@ -61,6 +64,12 @@ __device__ __forceinline__ void store_tile_at(const CUtensorMap* tm, uint32_t sr
                : "memory");
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(tm), "r"(col0 + 64),
                "r"(row0), "r"(src_saddr + 16384u)
+               : "memory");
+}
+// one fp32 panel (32 columns x 128 rows, 16 KB) -> columns [col0, col0 + 32) of a make_rows_map_f32 matrix
+__device__ __forceinline__ void store_panel_f32(const CUtensorMap* tm, uint32_t src_saddr, int col0, int row0) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(tm), "r"(col0), "r"(row0),
+               "r"(src_saddr)
                : "memory");
 }
 __device__ __forceinline__ void store_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
