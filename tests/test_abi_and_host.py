@@ -233,3 +233,31 @@ def test_probe_library_is_separate_and_exports_its_header():
     probe = lib.load_probe()
     for name in declared:
         assert hasattr(probe, name) and not hasattr(product, name), name
+
+
+def test_new_entry_points_validate_arguments_before_touching_the_gpu():
+    """aero_wgrad / aero_row_gemm / aero_thin_linear_*: bad arguments are refused with an error code and a message,
+    and an empty problem is a no-op -- all decided on the host, so this runs without a GPU."""
+    import ctypes as C
+    from aero_gnn_b200 import lib as L
+    lib = L.load()
+    one = C.c_void_p(16)                                        # any non-null, 16-byte aligned address: never dereferenced
+    assert lib.aero_wgrad_workspace_bytes(1000, 2, 1) > lib.aero_wgrad_workspace_bytes(1000, 1, 0) > 0
+    rc = lib.aero_wgrad(one, 128, 3, one, 10, one, None, None, 0, None, 0, one, 1 << 30, None)     # a_panels = 3
+    assert rc != 0 and b"aero_wgrad" in lib.aero_last_error()
+    rc = lib.aero_wgrad(one, 64, 1, one, 10, one, None, None, 0, None, 0, one, 1 << 30, None)      # lda < 128
+    assert rc != 0
+    rc = lib.aero_wgrad(one, 128, 1, one, 10, one, None, None, 0, None, 0, one, 8, None)           # workspace too small
+    assert rc != 0 and b"workspace" in lib.aero_last_error()
+    ptrs, lds = (C.c_void_p * 3)(16, 16, 16), (C.c_int64 * 3)(128, 128, 128)
+    rc = lib.aero_row_gemm(ptrs, lds, 2, one, 1, 2, None, None, 0, one, 256, 10, None)             # na and nb both > 1
+    assert rc != 0 and b"aero_row_gemm" in lib.aero_last_error()
+    rc = lib.aero_row_gemm(ptrs, lds, 1, one, 0, 3, None, None, 0, one, 128, 10, None)             # out_ld < 128 nb
+    assert rc != 0
+    assert lib.aero_row_gemm(ptrs, lds, 1, one, 0, 3, None, None, 0, one, 384, 0, None) == 0       # no rows: nothing to do
+    rc = lib.aero_thin_linear_fwd(one, 4, one, None, one, 10, 17, L.AERO_BF16, None)               # K > 16
+    assert rc != 0 and b"aero_thin_linear_fwd" in lib.aero_last_error()
+    rc = lib.aero_thin_linear_fwd(one, 2, one, None, one, 10, 4, L.AERO_BF16, None)                # ldx < K
+    assert rc != 0
+    assert lib.aero_thin_linear_fwd(one, 4, one, None, one, 0, 4, L.AERO_BF16, None) == 0
+    assert lib.aero_thin_linear_workspace_bytes(100000, 6) >= 128 * 7 * 4
