@@ -273,7 +273,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "edges/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_desc("c5", N, E), "parallelism": parallelism_desc("c5", world)},
+            "config": c5_config(N, E, world),      # the GPU arm's config, verbatim
             "cpu_baseline": {"value": r["value"], "unit": "edges/s", "cores": threads, "kind": r["kind"],
                              "sample": r["sample"], "step_ms_min_max": [r["ms_min"], r["ms_max"]]},
             "e2e": {"value": r["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -313,6 +313,12 @@ class Timer:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
+
+
+def c5_config(N, E, world):
+    """`config` of the default workload: identical in the GPU arm and in the reference arm."""
+    return {"workload": workload_desc("c5", N, E), "parallelism": parallelism_desc("c5", world),
+            "l2": "no flush between steps: a step streams >1.7 GB of latents (N = 1), far more than the 126 MB L2"}
 
 
 def graphed(step, world, dev, rank, want):
@@ -581,7 +587,7 @@ def bench_c5(args, rank, world, local, dev):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "edge_steps_per_s": 15 * value,
-            "config": {"workload": workload_desc("c5", N, E), "parallelism": parallelism_desc("c5", world)},
+            "config": c5_config(N, E, world),
             "run": {"l2": "inputs (>1.7 GB of latents per step) are larger than L2",
                     "path": "umma" if lib.load().aero_has_umma() and dt == torch.bfloat16 else "simt",
                     "launch": "one CUDA graph replay per step" if is_graph else "eager launches"},
@@ -671,7 +677,8 @@ def bench_c2(args, rank, world, local, dev):
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
                 "data": "synthetic",
-                "config": {"workload": workload_desc("c2", N, E), "parallelism": parallelism_desc("c2", world)},
+                "config": {"workload": workload_desc("c2", N, E), "parallelism": parallelism_desc("c2", world),
+                           "l2": "not flushed: 70 MB of latents per step are partly L2-resident (stated)"},
                 "run": {"launch": "one CUDA graph replay per step" if is_graph else "eager launches",
                         "l2": "70 MB of latents per step: partly L2-resident (stated, not flushed)",
                         "path": "umma" if lib.load().aero_has_umma() and dt == torch.bfloat16 else "simt",
@@ -740,7 +747,8 @@ def bench_c3(args, rank, world, local, dev):
         line = {"metric": "BSMS-MGN edges/sec (fwd+bwd)", "value": world * E / (ms * 1e-3), "unit": "edges/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": workload_desc("c3", N, E), "parallelism": parallelism_desc("c3", world)},
+                "config": {"workload": workload_desc("c3", N, E), "parallelism": parallelism_desc("c3", world),
+                           "l2": "not flushed: activations of the fine level (>200 MB per step) exceed L2, coarse levels do not (stated)"},
                 "run": {"launch": "one CUDA graph replay per step" if is_graph else "eager launches",
                         "hierarchy": "pool levels cached per mesh (content hash)",
                         "path": "umma" if lib.load().aero_has_umma() and dt == torch.bfloat16 else "simt"},
