@@ -199,6 +199,39 @@ __device__ __forceinline__ void fma4(float4& acc, float w, const float4& t) {
   acc.x = fmaf(w, t.x, acc.x); acc.y = fmaf(w, t.y, acc.y); acc.z = fmaf(w, t.z, acc.z); acc.w = fmaf(w, t.w, acc.w);
 }
 
+// edge weights, one LANE per edge (CSR slot k): w_k = sigmoid(W2 . relu(A[src_k] + B[dst_k] + w1_len * len_k) + b2).
+// The 64-wide dot product runs inside one thread (2 x 16 vector loads of the two half rows, 64 x 4 arithmetic
+// instructions) instead of being spread over a warp with a 5-step shuffle reduction per edge: ~9 warp instructions
+// per edge instead of ~25.  Consecutive slots share their receiver, so the B half-row loads of neighbouring lanes
+// coalesce; the A half rows are L2 / L1 gathers.  The weight is rounded to the storage dtype and stored in caller
+// order, exactly what the fused forward below stores when it computes the weights itself.
+template <typename T>
+__global__ void __launch_bounds__(256) wec_weight_kernel(WecArgs a) {
+  __shared__ float s_wl[WEC_HID], s_w2[WEC_HID];
+  if (threadIdx.x < WEC_HID) {
+    s_wl[threadIdx.x] = a.w1_len[threadIdx.x];
+    s_w2[threadIdx.x] = a.w2[threadIdx.x];
+  }
+  __syncthreads();
+  const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (k >= a.E) return;
+  const T* __restrict__ Q = reinterpret_cast<const T*>(a.Q);
+  const int64_t s = a.src[k], n = a.dst[k];
+  const float len = edge_len(a.pos, a.pos_dim, s, n);
+  const T* __restrict__ A = Q + s * a.ldq;
+  const T* __restrict__ B = Q + n * a.ldq + WEC_HID;
+  float sc = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < WEC_HID; j += 4) {
+    const float4 av = load4(A + j), bv = load4(B + j);
+    sc = fmaf(fmaxf(av.x + bv.x + s_wl[j] * len, 0.f), s_w2[j], sc);
+    sc = fmaf(fmaxf(av.y + bv.y + s_wl[j + 1] * len, 0.f), s_w2[j + 1], sc);
+    sc = fmaf(fmaxf(av.z + bv.z + s_wl[j + 2] * len, 0.f), s_w2[j + 2], sc);
+    sc = fmaf(fmaxf(av.w + bv.w + s_wl[j + 3] * len, 0.f), s_w2[j + 3], sc);
+  }
+  store1(reinterpret_cast<T*>(a.w) + a.perm[k], round_to<T>(sigmoid_fast(sc + a.b2[0])));
+}
+
 // forward: out[n] = sum_k w_k * T[src_k] over the receiver's CSR segment; w_k from the edge-weight MLP (COMPUTE) or given
 template <typename T, bool COMPUTE>
 __global__ void __launch_bounds__(WEC_THREADS) wec_fwd_kernel(WecArgs a) {
@@ -606,7 +639,16 @@ template <typename T>
 static int wec_fwd_t(const aero_wec_desc* d, cudaStream_t st) {
   WecArgs a = wec_args(d);
   dim3 grid((unsigned)cdiv(d->N, WEC_THREADS / 32));
-  if (d->compute_w) wec_fwd_kernel<T, true><<<grid, WEC_THREADS, 0, st>>>(a);
+  // compute_w: the weights come from a lane-per-edge pass, the aggregation then reads them like given weights
+  // (AERO_WEC_FUSED=1: the earlier single kernel that spreads each edge's 64-wide dot product over a warp)
+  static const bool fused = [] { const char* e = getenv("AERO_WEC_FUSED"); return e && e[0] == '1'; }();
+  if (d->compute_w && !fused) {
+    if (d->E > 0) {
+      wec_weight_kernel<T><<<grid1(d->E), 256, 0, st>>>(a);
+      AERO_LAUNCH_CHECK();
+    }
+    wec_fwd_kernel<T, false><<<grid, WEC_THREADS, 0, st>>>(a);
+  } else if (d->compute_w) wec_fwd_kernel<T, true><<<grid, WEC_THREADS, 0, st>>>(a);
   else wec_fwd_kernel<T, false><<<grid, WEC_THREADS, 0, st>>>(a);
   AERO_LAUNCH_CHECK();
   return AERO_OK;
